@@ -1,0 +1,178 @@
+// psb200 — Blackwell-native Gaussian-splatting rasterizer / trainer step (sm_100a).
+// Shared device helpers. Nothing here depends on torch; everything is plain CUDA.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <cuda_runtime.h>
+
+#define PSB_TILE_X 16
+#define PSB_TILE_Y 16
+#define PSB_TILE_PIX (PSB_TILE_X * PSB_TILE_Y)
+
+// Error plumbing: every host entry point returns 0 on success or a negative psb error code and keeps
+// the CUDA error string retrievable through psb_last_error().
+namespace psb {
+
+void set_error(const char* what, cudaError_t e, const char* file, int line);
+void set_error_msg(const char* what);
+
+#define PSB_CUDA_OK(expr)                                              \
+	do {                                                               \
+		cudaError_t _e = (expr);                                       \
+		if (_e != cudaSuccess) {                                       \
+			psb::set_error(#expr, _e, __FILE__, __LINE__);             \
+			return -2;                                                 \
+		}                                                              \
+	} while (0)
+
+#define PSB_LAUNCH_OK()                                                \
+	do {                                                               \
+		cudaError_t _e = cudaGetLastError();                           \
+		if (_e != cudaSuccess) {                                       \
+			psb::set_error("kernel launch", _e, __FILE__, __LINE__);   \
+			return -2;                                                 \
+		}                                                              \
+	} while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// Per-Gaussian screen-space record produced by the forward preprocess and consumed (as one
+// 48-byte bulk copy) by the tile kernels. 16-byte aligned, three float4 lanes:
+//   q0 = (mean2D.x, mean2D.y, conic.a, conic.b)
+//   q1 = (conic.c,  opacity,  rgb.r,   rgb.g)
+//   q2 = (rgb.b,    depth,    radius (int bits), flags (bit0..2 = SH clamp per channel))
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) GaussRec {
+	float4 q0, q1, q2;
+};
+static_assert(sizeof(GaussRec) == 48, "GaussRec must be 48 bytes");
+
+// Camera block passed by value to the per-Gaussian kernels. The 4x4 matrices stay where the caller put
+// them (device memory, column-major m[4*c + r] exactly as the reference passes them, e.g.
+// reference rasterize_points.cu:104-106) so that no host round trip is needed at the boundary.
+struct Camera {
+	const float* view;    // world -> view, 16 floats
+	const float* proj;    // world -> clip (view * projection), 16 floats
+	const float* campos;  // camera centre, 3 floats
+	float tan_fovx, tan_fovy;
+	float focal_x, focal_y;
+	int W, H;
+	int grid_x, grid_y;
+};
+
+// Spherical-harmonics basis constants (real SH up to degree 3, the standard 3DGS convention; same
+// values as reference cuda_rasterizer/auxiliary.h:22-39). constexpr scalars: usable in device code.
+constexpr float kSH_C0 = 0.28209479177387814f;
+constexpr float kSH_C1 = 0.4886025119029199f;
+constexpr float kSH_C2_0 = 1.0925484305920792f;
+constexpr float kSH_C2_1 = -1.0925484305920792f;
+constexpr float kSH_C2_2 = 0.31539156525252005f;
+constexpr float kSH_C2_3 = -1.0925484305920792f;
+constexpr float kSH_C2_4 = 0.5462742152960396f;
+constexpr float kSH_C3_0 = -0.5900435899266435f;
+constexpr float kSH_C3_1 = 2.890611442640554f;
+constexpr float kSH_C3_2 = -0.4570457994644658f;
+constexpr float kSH_C3_3 = 0.3731763325901154f;
+constexpr float kSH_C3_4 = -0.4570457994644658f;
+constexpr float kSH_C3_5 = 1.445305721320277f;
+constexpr float kSH_C3_6 = -0.5900435899266435f;
+
+// ---- tiny column-major 3x3 (M[c][r] at m[3c+r]); products are written as three-term sums in the
+// order  a[0][r]*b[c][0] + a[1][r]*b[c][1] + a[2][r]*b[c][2]  so nvcc contracts them exactly like the
+// reference's glm expressions (bit-exact radii / tile rects depend on it; verified on B200 against the
+// reference build, tests/test_parity_ref_gpu.py).
+struct Mat3 {
+	float m[9];
+	__device__ __forceinline__ float& operator()(int c, int r) { return m[3 * c + r]; }
+	__device__ __forceinline__ float operator()(int c, int r) const { return m[3 * c + r]; }
+};
+__device__ __forceinline__ Mat3 mat3_mul(const Mat3& a, const Mat3& b)
+{
+	Mat3 r;
+#pragma unroll
+	for (int c = 0; c < 3; c++)
+#pragma unroll
+		for (int rr = 0; rr < 3; rr++)
+			r(c, rr) = a(0, rr) * b(c, 0) + a(1, rr) * b(c, 1) + a(2, rr) * b(c, 2);
+	return r;
+}
+__device__ __forceinline__ Mat3 mat3_transpose(const Mat3& a)
+{
+	Mat3 r;
+#pragma unroll
+	for (int c = 0; c < 3; c++)
+#pragma unroll
+		for (int rr = 0; rr < 3; rr++) r(c, rr) = a(rr, c);
+	return r;
+}
+
+__device__ __forceinline__ float3 xform4x3(const float3 p, const float* m)
+{
+	return make_float3(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
+	                   m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+	                   m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14]);
+}
+__device__ __forceinline__ float4 xform4x4(const float3 p, const float* m)
+{
+	return make_float4(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
+	                   m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+	                   m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14],
+	                   m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15]);
+}
+
+// Pixel centre from NDC. Evaluated in double like the reference (cuda_rasterizer/auxiliary.h:41-44):
+// the tile rectangle, and therefore every (tile|depth) key, depends on this rounding.
+__device__ __forceinline__ float ndc_to_pix(float v, int S) { return ((v + 1.0) * S - 1.0) * 0.5; }
+
+// Tile rectangle of a splat (reference semantics, cuda_rasterizer/auxiliary.h:46-56): truncation toward
+// zero, then clamp to [0, grid].
+__device__ __forceinline__ void tile_rect(float px, float py, int max_radius, int gx, int gy,
+                                          int& x0, int& y0, int& x1, int& y1)
+{
+	x0 = min(gx, max(0, (int)((px - max_radius) / PSB_TILE_X)));
+	y0 = min(gy, max(0, (int)((py - max_radius) / PSB_TILE_Y)));
+	x1 = min(gx, max(0, (int)((px + max_radius + PSB_TILE_X - 1) / PSB_TILE_X)));
+	y1 = min(gy, max(0, (int)((py + max_radius + PSB_TILE_Y - 1) / PSB_TILE_Y)));
+}
+
+// ---- async-copy / mbarrier PTX wrappers (TMA 1-D bulk copies) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_LOOP:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra DONE;\n"
+		"bra WAIT_LOOP;\n"
+		"DONE:\n"
+		"}\n" ::"r"(smem_u32(bar)),
+		"r"(parity)
+		: "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP); bytes must be a multiple of 16 and
+// both addresses 16-byte aligned. Completion is signalled on the mbarrier as transaction bytes.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+	             "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+	             : "memory");
+}
+
+}  // namespace psb

@@ -1,0 +1,330 @@
+// Forward pipeline up to the per-tile instance lists:
+//   preprocess (project, covariance -> conic, SH -> RGB, tile rectangle)          [per Gaussian]
+//   depth sort of the Gaussians (4 x 8-bit onesweep passes on the float bits)     [per Gaussian]
+//   exclusive scan of tiles_touched in depth order  -> instance offsets, num_rendered
+//   emit (tile id, Gaussian) instances in depth order
+//   stable sort of the instances by tile id (ceil(log2 #tiles) bits, 1-2 onesweep passes)
+//   tile ranges
+//
+// The reference sorts every instance on a 64-bit (tile | depth) key in ~6 radix passes
+// (reference rasterizer_impl.cu:70-111, 300-308). Sorting the P Gaussians by depth ONCE and then
+// stably partitioning the N instances by tile yields exactly the same order — ties on (tile, depth)
+// stay in ascending Gaussian index in both — with 4 passes over P plus 2 passes over N of 8-byte
+// records instead of 6 passes over N of 12-byte records.
+#include "psb_geom.cuh"
+#include "psb_state.h"
+#include "psb_kernels.h"
+
+namespace psb {
+
+// ------------------------------------------------------------------------------------------------
+// Preprocess. One thread per Gaussian. Mirrors the per-Gaussian contract of reference
+// forward.cu:155-256 (near cull at view z <= 0.2, det == 0 cull, zero-area rect cull; culled
+// Gaussians only get radii = tiles_touched = 0).
+// RAW = true: inputs are the raw trainer parameters (log-scales, unnormalised quaternions, opacity
+// logits, SH split into dc/rest); the activations of reference gaussian_model.cpp:48-71 are applied
+// here instead of by five separate elementwise kernels and a 192 B/Gaussian concatenation.
+// ------------------------------------------------------------------------------------------------
+template <bool RAW>
+__global__ void __launch_bounds__(128) preprocess_fwd_kernel(GaussIn in, Camera cam, int* __restrict__ radii_out, GeomState geom)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= in.P) return;
+
+	if (radii_out) radii_out[idx] = 0;
+	geom.tiles_touched[idx] = 0;
+	geom.depth_key[0][idx] = 0xFFFFFFFFu;
+
+	const float3 p_orig = make_float3(in.means3D[3 * idx], in.means3D[3 * idx + 1], in.means3D[3 * idx + 2]);
+	const float3 p_view = xform4x3(p_orig, cam.view);
+	if (p_view.z <= 0.2f) return;
+
+	const float4 p_hom = xform4x4(p_orig, cam.proj);
+	const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+	const float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
+
+	float cov3D[6];
+	if (in.cov3D_precomp != nullptr) {
+#pragma unroll
+		for (int i = 0; i < 6; i++) cov3D[i] = in.cov3D_precomp[6 * idx + i];
+	} else {
+		float3 s = make_float3(in.scales[3 * idx], in.scales[3 * idx + 1], in.scales[3 * idx + 2]);
+		float4 q = reinterpret_cast<const float4*>(in.rotations)[idx];
+		if (RAW) {
+			s = make_float3(expf(s.x), expf(s.y), expf(s.z));
+			const float n = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+			q = make_float4(q.x / n, q.y / n, q.z / n, q.w / n);
+		}
+		cov3d_from_scale_rot(s, in.scale_modifier, q, cov3D);
+	}
+
+	Cov2DTerms ct;
+	cov2d_terms(p_orig, cam.focal_x, cam.focal_y, cam.tan_fovx, cam.tan_fovy, cov3D, cam.view, ct);
+	ct.cov(0, 0) += 0.3f;
+	ct.cov(1, 1) += 0.3f;
+	const float3 cov = make_float3(float(ct.cov(0, 0)), float(ct.cov(0, 1)), float(ct.cov(1, 1)));
+
+	const float det = (cov.x * cov.z - cov.y * cov.y);
+	if (det == 0.0f) return;
+	const float det_inv = 1.f / det;
+	const float3 conic = make_float3(cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv);
+
+	const float mid = 0.5f * (cov.x + cov.z);
+	const float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
+	const float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+	const float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
+	const float2 point_image = make_float2(ndc_to_pix(p_proj.x, cam.W), ndc_to_pix(p_proj.y, cam.H));
+	int x0, y0, x1, y1;
+	tile_rect(point_image.x, point_image.y, (int)my_radius, cam.grid_x, cam.grid_y, x0, y0, x1, y1);
+	if ((x1 - x0) * (y1 - y0) == 0) return;
+
+	float3 rgb;
+	uint32_t clamp_bits = 0;
+	if (in.colors_precomp != nullptr) {
+		rgb = make_float3(in.colors_precomp[3 * idx], in.colors_precomp[3 * idx + 1], in.colors_precomp[3 * idx + 2]);
+	} else {
+		const float3 campos = make_float3(cam.campos[0], cam.campos[1], cam.campos[2]);
+		float sh[48];
+		const int ncoef = (in.D + 1) * (in.D + 1);
+		if (RAW) {
+			sh[0] = in.sh_dc[3 * idx]; sh[1] = in.sh_dc[3 * idx + 1]; sh[2] = in.sh_dc[3 * idx + 2];
+			const float* rest = in.sh_rest + (size_t)idx * (in.M - 1) * 3;
+#pragma unroll
+			for (int k = 3; k < 48; k++) sh[k] = (k < ncoef * 3) ? rest[k - 3] : 0.f;
+		} else {
+			const float* row = in.shs + (size_t)idx * in.M * 3;
+			if (in.sh_vec4) {
+#pragma unroll
+				for (int k = 0; k < 12; k++) {
+					float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+					if (k * 4 < ncoef * 3) v = reinterpret_cast<const float4*>(row)[k];
+					sh[4 * k] = v.x; sh[4 * k + 1] = v.y; sh[4 * k + 2] = v.z; sh[4 * k + 3] = v.w;
+				}
+			} else {
+#pragma unroll
+				for (int k = 0; k < 48; k++) sh[k] = (k < ncoef * 3) ? row[k] : 0.f;
+			}
+		}
+		rgb = sh_to_rgb(in.D, p_orig, campos, sh, clamp_bits);
+	}
+
+	float opacity = in.opacities[idx];
+	if (RAW) opacity = 1.0f / (1.0f + expf(-opacity));
+
+	const int radius_i = (int)my_radius;
+	GaussRec r;
+	r.q0 = make_float4(point_image.x, point_image.y, conic.x, conic.y);
+	r.q1 = make_float4(conic.z, opacity, rgb.x, rgb.y);
+	r.q2 = make_float4(rgb.z, p_view.z, __int_as_float(radius_i), __uint_as_float(clamp_bits));
+	geom.rec[idx] = r;
+	geom.depth_key[0][idx] = __float_as_uint(p_view.z);
+	if (radii_out) radii_out[idx] = radius_i;
+	geom.rect[idx] = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
+	geom.tiles_touched[idx] = (uint32_t)((y1 - y0) * (x1 - x0));
+}
+
+// z > 0.2 visibility test only (reference rasterizer_impl.cu:54-66, auxiliary.h:139-164).
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view, uint8_t* __restrict__ present)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= P) return;
+	const float3 p = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+	const float3 pv = xform4x3(p, view);
+	present[idx] = pv.z > 0.2f ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Single-pass exclusive scan (decoupled look-back) of tiles_touched taken in depth-sorted order.
+// status word: 2 flag bits | 30-bit value. counters[0] <- total (num_rendered).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles_touched,
+                                                                    uint32_t* __restrict__ offsets, uint32_t* __restrict__ counters,
+                                                                    uint32_t* __restrict__ status)
+{
+	__shared__ uint32_t s_warp[SCAN_THREADS / 32];
+	__shared__ uint32_t s_tile, s_prefix;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid == 0) s_tile = atomicAdd(&counters[1], 1u);
+	__syncthreads();
+	const uint32_t tile = s_tile;
+	const int base = (int)tile * SCAN_TILE + tid * SCAN_ITEMS;
+	uint32_t v[SCAN_ITEMS];
+	uint32_t sum = 0;
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; i++) {
+		const int j = base + i;
+		v[i] = (j < P) ? tiles_touched[order[j]] : 0u;
+		sum += v[i];
+	}
+	uint32_t inc = sum;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+		if (lane >= o) inc += u;
+	}
+	if (lane == 31) s_warp[warp] = inc;
+	__syncthreads();
+	uint32_t wb = 0, block_total = 0;
+#pragma unroll
+	for (int i = 0; i < SCAN_THREADS / 32; i++) {
+		if (i < warp) wb += s_warp[i];
+		block_total += s_warp[i];
+	}
+	if (tid == 0) {
+		uint32_t excl = 0;
+		volatile uint32_t* st = status;
+		if (tile == 0) {
+			st[0] = (2u << 30) | block_total;
+		} else {
+			st[tile] = (1u << 30) | block_total;
+			int p = (int)tile - 1;
+			while (true) {
+				uint32_t s;
+				do { s = st[p]; } while ((s >> 30) == 0u);
+				excl += s & ((1u << 30) - 1u);
+				if ((s >> 30) == 2u) break;
+				p--;
+			}
+			st[tile] = (2u << 30) | ((excl + block_total) & ((1u << 30) - 1u));
+		}
+		s_prefix = excl;
+		if ((int)(tile + 1) * SCAN_TILE >= P) counters[0] = excl + block_total;
+	}
+	__syncthreads();
+	uint32_t run = s_prefix + wb + inc - sum;
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; i++) {
+		const int j = base + i;
+		if (j < P) offsets[j] = run;
+		run += v[i];
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Emit one (tile id, Gaussian) instance per overlapped tile, Gaussians taken in depth order, tiles of
+// one Gaussian row-major (y outer, x inner) like reference rasterizer_impl.cu:95-108. Small rectangles
+// are written by the owning lane, large ones cooperatively by the warp.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint2* __restrict__ rect,
+                                                             const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ offsets,
+                                                             uint32_t* __restrict__ tile_key, uint32_t* __restrict__ inst, int grid_x,
+                                                             uint32_t capacity)
+{
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	uint32_t g = 0, tt = 0, off = 0, x0 = 0, y0 = 0, w = 1;
+	if (j < P) {
+		g = order[j];
+		tt = tiles_touched[g];
+		if (tt > 0) {
+			const uint2 r = rect[g];
+			x0 = r.x & 0xFFFFu; y0 = r.x >> 16;
+			w = (r.y & 0xFFFFu) - x0;
+			off = offsets[j];
+			if (off + tt > capacity) tt = 0;  // cannot happen when capacity >= num_rendered; guards the arena mode
+		}
+	}
+	constexpr uint32_t SMALL = 6;
+	if (tt > 0 && tt <= SMALL) {
+		uint32_t tx = x0, ty = y0;
+		for (uint32_t k = 0; k < tt; k++) {
+			tile_key[off + k] = ty * grid_x + tx;
+			inst[off + k] = g;
+			if (++tx == x0 + w) { tx = x0; ty++; }
+		}
+	}
+	uint32_t big = __ballot_sync(0xffffffffu, tt > SMALL);
+	while (big) {
+		const int src = __ffs(big) - 1;
+		big &= big - 1;
+		const uint32_t bg = __shfl_sync(0xffffffffu, g, src);
+		const uint32_t btt = __shfl_sync(0xffffffffu, tt, src);
+		const uint32_t boff = __shfl_sync(0xffffffffu, off, src);
+		const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src);
+		const uint32_t by0 = __shfl_sync(0xffffffffu, y0, src);
+		const uint32_t bw = __shfl_sync(0xffffffffu, w, src);
+		for (uint32_t k = lane; k < btt; k += 32) {
+			const uint32_t ty = by0 + k / bw, tx = bx0 + k % bw;
+			tile_key[boff + k] = ty * grid_x + tx;
+			inst[boff + k] = bg;
+		}
+	}
+}
+
+// Start/end of every tile in the tile-sorted instance list (semantics of reference
+// rasterizer_impl.cu:116-138; ranges must be zeroed beforehand so untouched tiles read {0,0}).
+__global__ void tile_ranges_kernel(const uint32_t* __restrict__ n_dev, uint32_t n_host, const uint32_t* __restrict__ tile_key_sorted,
+                                   uint2* __restrict__ ranges)
+{
+	const uint32_t n = n_dev ? min(*n_dev, n_host) : n_host;
+	const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= n) return;
+	const uint32_t cur = tile_key_sorted[idx];
+	if (idx == 0) ranges[cur].x = 0;
+	else {
+		const uint32_t prev = tile_key_sorted[idx - 1];
+		if (cur != prev) { ranges[prev].y = idx; ranges[cur].x = idx; }
+	}
+	if (idx == n - 1) ranges[cur].y = n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host orchestration
+// ------------------------------------------------------------------------------------------------
+int launch_preprocess(const GaussIn& in, const Camera& cam, int* radii_out, const GeomState& geom, bool raw, cudaStream_t stream)
+{
+	if (in.P == 0) return 0;
+	const int grid = cdiv(in.P, 128);
+	if (raw) preprocess_fwd_kernel<true><<<grid, 128, 0, stream>>>(in, cam, radii_out, geom);
+	else preprocess_fwd_kernel<false><<<grid, 128, 0, stream>>>(in, cam, radii_out, geom);
+	PSB_LAUNCH_OK();
+	return 0;
+}
+
+int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t stream)
+{
+	if (P == 0) return 0;
+	mark_visible_kernel<<<cdiv(P, 256), 256, 0, stream>>>(P, means3D, view, present);
+	PSB_LAUNCH_OK();
+	return 0;
+}
+
+// Depth sort + offsets scan. After this geom.order[0] is the depth-sorted permutation,
+// geom.offsets the instance offsets and geom.counters[0] = num_rendered.
+int launch_depth_sort_and_scan(int P, GeomState& geom, cudaStream_t stream)
+{
+	if (P == 0) return 0;
+	PSB_CUDA_OK(cudaMemsetAsync(geom.counters, 0, 32 * sizeof(uint32_t), stream));
+	PSB_CUDA_OK(cudaMemsetAsync(geom.scan_status, 0, ((size_t)(P + SCAN_TILE - 1) / SCAN_TILE + 1) * sizeof(uint32_t), stream));
+	const SortPlan plan = make_sort_plan(32);
+	int rc = radix_sort_pairs(geom.depth_key, geom.order, /*iota_vals=*/true, nullptr, (size_t)P, plan, geom.sort_scratch,
+	                          geom.sort_scratch_bytes, stream);
+	if (rc) return rc;
+	// 4 passes -> result back in buffer 0
+	scan_offsets_kernel<<<cdiv(P, SCAN_TILE), SCAN_THREADS, 0, stream>>>(P, geom.order[0], geom.tiles_touched, geom.offsets, geom.counters,
+	                                                                    geom.scan_status);
+	PSB_LAUNCH_OK();
+	return 0;
+}
+
+// Emit + tile sort + ranges. `capacity` = size the binning chunk was carved for; n_dev (device) holds
+// the true instance count when the host does not know it (arena mode), else pass nullptr and n_host = R.
+int launch_binning(int P, const Camera& cam, const GeomState& geom, BinState& bin, const ImgState& img, const uint32_t* n_dev,
+                   size_t n_host, cudaStream_t stream)
+{
+	const int num_tiles = cam.grid_x * cam.grid_y;
+	PSB_CUDA_OK(cudaMemsetAsync(img.ranges, 0, (size_t)num_tiles * sizeof(uint2), stream));
+	if (P == 0 || n_host == 0) return 0;
+	emit_instances_kernel<<<cdiv(P, 256), 256, 0, stream>>>(P, geom.order[0], geom.rect, geom.tiles_touched, geom.offsets, bin.tile_key[0],
+	                                                       bin.inst[0], cam.grid_x, (uint32_t)n_host);
+	PSB_LAUNCH_OK();
+	const SortPlan plan = make_sort_plan(tile_id_bits(num_tiles));
+	int rc = radix_sort_pairs(bin.tile_key, bin.inst, false, n_dev, n_host, plan, bin.sort_scratch, bin.sort_scratch_bytes, stream);
+	if (rc) return rc;
+	const int res = plan.npass & 1;
+	tile_ranges_kernel<<<(unsigned)((n_host + 255) / 256), 256, 0, stream>>>(n_dev, (uint32_t)n_host, bin.tile_key[res], img.ranges);
+	PSB_LAUNCH_OK();
+	return 0;
+}
+
+}  // namespace psb

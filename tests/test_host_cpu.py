@@ -1,0 +1,37 @@
+"""CPU: host-side logic — camera conventions of the synthetic generator against the reference's formulas."""
+import math
+
+import numpy as np
+
+import photo_slam_b200.synthetic as syn
+
+
+def test_camera_matrices_follow_reference_conventions():
+    rng = np.random.default_rng(0)
+    R, t = syn.random_pose(rng)
+    W, H, fx, fy = syn.CAMERAS["replica"]
+    cam = syn.make_camera(W, H, fx, fy, R, t)
+    vm = cam["viewmatrix"].reshape(4, 4)      # row-major tensor = Rt^T  (gaussian_keyframe.cpp:122-125)
+    assert np.allclose(vm.T[:3, :3], R, atol=1e-6) and np.allclose(vm.T[:3, 3], t, atol=1e-6)
+    pm = cam["projmatrix"].reshape(4, 4)      # (P @ Rt)^T  (gaussian_keyframe.cpp:138-139)
+    p = np.array([0.3, -0.2, 2.0, 1.0])
+    clip = p @ pm                             # row-vector convention of the transposed matrices
+    cam_pt = R @ p[:3] + t
+    assert np.isclose(clip[3], cam_pt[2], rtol=1e-5)                       # P32 = 1  -> w = view z
+    assert np.isclose(clip[0] / clip[3], cam_pt[0] / cam_pt[2] / float(cam["tanfovx"]), rtol=1e-5)
+    assert np.isclose(float(cam["tanfovx"]), W / (2 * fx), rtol=1e-6)      # tan(fov/2), fov = 2 atan(W / 2f)  (graphics_utils.h:47-50)
+    assert np.allclose(R @ cam["campos"] + t, 0, atol=1e-5)                # camera centre maps to the origin of the view frame
+    # memory convention used by the kernels: m[4*c + r] is row r, column c of Rt
+    flat = cam["viewmatrix"]
+    assert np.isclose(flat[4 * 3 + 1], t[1], atol=1e-6)
+
+
+def test_scene_statistics():
+    W, H, fx, fy = syn.CAMERAS["tum"]
+    cam = syn.make_camera(W, H, fx, fy)
+    sc = syn.make_scene(20000, cam, seed=0)
+    assert sc["features_rest"].shape == (20000, 15, 3) and sc["features_dc"].shape == (20000, 1, 3)
+    z = sc["xyz"][:, 2]
+    assert 0.03 < np.mean(z <= 0.2) < 0.07                                  # ~5 % behind the near plane
+    sig_px = np.exp(sc["scaling"]).mean(1) * fx / np.maximum(np.abs(z), 0.5)
+    assert 2.0 < np.median(sig_px) < 3.5

@@ -1,0 +1,121 @@
+"""CPU: the oracle's own building blocks against independent statements of the same math.
+
+The reference's loss, Adam and activations ARE LibTorch ops (arithmetic living in LibTorch), so
+the oracle's C restatements are pinned here against the same ops run by torch on CPU."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle_c
+import photo_slam_b200.synthetic as syn
+
+
+def _torch_loss(img, gt, lam=0.2):
+    """loss_utils::l1_loss / ssim restated with torch ops exactly as reference include/loss_utils.h:28-124."""
+    x = torch.from_numpy(img).clone().requires_grad_(True)
+    y = torch.from_numpy(gt)
+    gauss = torch.tensor([math.exp(-(i - 5) ** 2 / (2 * 1.5 ** 2)) for i in range(11)], dtype=torch.float32)
+    gauss = (gauss / gauss.sum()).unsqueeze(1)
+    win = gauss.mm(gauss.t()).float().unsqueeze(0).unsqueeze(0).expand(3, 1, 11, 11).contiguous()
+    a, b = x.unsqueeze(0), y.unsqueeze(0)
+    mu1, mu2 = F.conv2d(a, win, padding=5, groups=3), F.conv2d(b, win, padding=5, groups=3)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    s1 = F.conv2d(a * a, win, padding=5, groups=3) - mu1_sq
+    s2 = F.conv2d(b * b, win, padding=5, groups=3) - mu2_sq
+    s12 = F.conv2d(a * b, win, padding=5, groups=3) - mu1_mu2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    ssim = (((2 * mu1_mu2 + C1) * (2 * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2))).mean()
+    l1 = (x - y).abs().mean()
+    loss = (1.0 - lam) * l1 + lam * (1.0 - ssim)
+    loss.backward()
+    return loss.item(), l1.item(), ssim.item(), x.grad.numpy()
+
+
+@pytest.mark.parametrize("H,W", [(37, 53), (16, 16), (8, 40)])
+def test_loss_and_gradient_match_torch(H, W):
+    rng = np.random.default_rng(H * W)
+    img = rng.uniform(0, 1, (3, H, W)).astype(np.float32)
+    gt = np.clip(img + rng.normal(0, 0.2, (3, H, W)), 0, 1).astype(np.float32)
+    v, l1, ss, g = oracle_c.loss(img, gt)
+    tv, tl1, tss, tg = _torch_loss(img, gt)
+    assert abs(v - tv) < 1e-5 and abs(l1 - tl1) < 1e-6 and abs(ss - tss) < 1e-5
+    assert np.linalg.norm(g - tg) / np.linalg.norm(tg) < 1e-4
+
+
+def test_adam_matches_torch_single_tensor_adam():
+    rng = np.random.default_rng(0)
+    p0 = rng.normal(size=1000).astype(np.float32)
+    p = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    opt = torch.optim.Adam([p], lr=0.0, eps=1e-15, foreach=False, fused=False)
+    opt.param_groups[0]["lr"] = 2.5e-3
+    pn, m, v = p0.copy(), np.zeros_like(p0), np.zeros_like(p0)
+    for t in range(1, 6):
+        g = rng.normal(size=1000).astype(np.float32) * (0.0 if t == 3 else 1e-3)   # a zero-gradient step still moves p (momentum)
+        p.grad = torch.from_numpy(g.copy())
+        opt.step()
+        pn, m, v = oracle_c.adam(pn, g, m, v, 2.5e-3, t)
+        assert np.allclose(pn, p.detach().numpy(), rtol=2e-6, atol=1e-9), t
+
+
+def test_activations_backward_match_torch_autograd():
+    import ctypes as C
+    rng = np.random.default_rng(1)
+    P = 257
+    o_raw = rng.normal(0, 1.5, (P, 1)).astype(np.float32)
+    s_raw = rng.normal(-4, 0.5, (P, 3)).astype(np.float32)
+    r_raw = rng.normal(size=(P, 4)).astype(np.float32)
+    go, gs, gr = (rng.normal(size=s).astype(np.float32) for s in ((P, 1), (P, 3), (P, 4)))
+    to, ts, tr = (torch.from_numpy(a.copy()).requires_grad_(True) for a in (o_raw, s_raw, r_raw))
+    (torch.sigmoid(to) * torch.from_numpy(go)).sum().backward()
+    (torch.exp(ts) * torch.from_numpy(gs)).sum().backward()
+    (F.normalize(tr) * torch.from_numpy(gr)).sum().backward()
+    L = oracle_c.lib()
+    out = [np.zeros_like(o_raw), np.zeros_like(s_raw), np.zeros_like(r_raw)]
+    L.orc_activations_backward(C.c_int(P), oracle_c._p(o_raw), oracle_c._p(s_raw), oracle_c._p(r_raw), oracle_c._p(go), oracle_c._p(gs),
+                               oracle_c._p(gr), oracle_c._p(out[0]), oracle_c._p(out[1]), oracle_c._p(out[2]))
+    for a, t in zip(out, (to, ts, tr)):
+        assert np.allclose(a, t.grad.numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_forward_structural_properties():
+    rng = np.random.default_rng(4)
+    R, t = syn.random_pose(rng)
+    cam = syn.make_camera(203, 117, 165.0, 165.0, R, t)
+    sc = syn.make_scene(4000, cam, seed=2, scale_px=5.0)
+    act = syn.activate(sc)
+    f = oracle_c.forward(cam, act, D=3, bg=(0.0, 0.0, 0.0))
+    N = f["num_rendered"]
+    assert N == int(f["tiles_touched"].sum()) and N > 0
+    assert np.all(np.diff(f["keys"].astype(np.uint64)) >= 0) or np.all(f["keys"][1:] >= f["keys"][:-1])      # sortedness
+    assert sorted(f["values"].tolist()) == sorted(np.repeat(np.arange(4000), f["tiles_touched"]).tolist())  # a permutation of the instances
+    r = f["ranges"]
+    touched = r[:, 1] > r[:, 0]
+    assert (r[touched, 1] - r[touched, 0]).sum() == N                                                        # ranges partition the list
+    assert np.all((f["radii"] > 0) == (f["tiles_touched"] > 0))
+    assert f["n_contrib"].max() <= (r[:, 1] - r[:, 0]).max()
+    assert np.all((f["final_T"] > 0) & (f["final_T"] <= 1))
+    # culled Gaussians: behind the near plane <=> not visible
+    vis = oracle_c.mark_visible(act["means3D"], cam)
+    assert np.all(vis[f["radii"] > 0])
+    # backward is linear in dL/dpix
+    d1 = rng.normal(size=(3, 117, 203)).astype(np.float32) * 1e-3
+    b1 = oracle_c.backward(cam, act, f, d1)
+    b2 = oracle_c.backward(cam, act, f, 2 * d1)
+    for k in b1:
+        assert np.allclose(2 * b1[k], b2[k], rtol=2e-4, atol=1e-9), k
+    # rows of invisible Gaussians stay zero
+    inv = f["radii"] <= 0
+    for k in b1:
+        assert not np.any(b1[k][inv]), k
+
+
+def test_knn_matches_bruteforce_numpy():
+    rng = np.random.default_rng(2)
+    pts = rng.normal(size=(300, 3)).astype(np.float32)
+    d = ((pts[:, None, :] - pts[None, :, :]) ** 2).sum(-1)
+    np.fill_diagonal(d, np.inf)
+    ref = np.sort(d, axis=1)[:, :3].mean(1)
+    assert np.allclose(oracle_c.knn_mean_dist2(pts), ref, rtol=1e-5)

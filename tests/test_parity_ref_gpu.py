@@ -1,0 +1,265 @@
+"""-m gpu parity tests: psb200 (through its C-ABI) vs the reference's OWN kernels (oracle/_ref, compiled
+unmodified for sm_100a) on the same seeded inputs, same B200.
+
+Gates: bit-exact radii, tiles_touched, num_rendered, sorted (tile|depth) keys and values,
+tile ranges, n_contrib; float tensors within 1e-4 relative (mask radii > 0)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_close, scene_tensors
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    import ref_gpu
+    from photo_slam_b200 import rasterizer
+    if not ref_gpu.available():
+        pytest.skip("oracle/_ref/libref_rasterizer.so not built")
+    return rasterizer, ref_gpu
+
+
+def _run_both(g, c, D, bg, colors=None, cov3D=None, scale_modifier=1.0):
+    rasterizer, ref_gpu = _mods()
+    dev = g["means3D"].device
+    empty = torch.empty(0, device=dev)
+    sh = empty if colors is not None else g["shs"]
+    col = colors if colors is not None else empty
+    sca = empty if cov3D is not None else g["scales"]
+    rot = empty if cov3D is not None else g["rotations"]
+    cov = cov3D if cov3D is not None else empty
+    args = (bg, g["means3D"], col, g["opacities"], sca, rot, scale_modifier, cov, c["viewmatrix"], c["projmatrix"],
+            c["tanfovx"], c["tanfovy"], c["H"], c["W"], sh, D, c["campos"], False)
+    mine = rasterizer.RasterizeGaussiansCUDA(*args)
+    ref = ref_gpu.rasterize_forward(*args)
+    torch.cuda.synchronize()
+    return mine, ref, (sh, col, sca, rot, cov)
+
+
+def _export_mine(P, R, W, H, geom, binning, img):
+    from photo_slam_b200 import _lib
+    L = _lib.lib()
+    dev = geom.device
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    o = dict(depths=torch.zeros(P, device=dev), means2D=torch.zeros(P, 2, device=dev), conic_opacity=torch.zeros(P, 4, device=dev),
+             rgb=torch.zeros(P, 3, device=dev), clamped=torch.zeros(P, 3, dtype=torch.uint8, device=dev),
+             tiles_touched=torch.zeros(P, dtype=torch.int32, device=dev), keys_sorted=torch.zeros(max(R, 1), dtype=torch.int64, device=dev),
+             values_sorted=torch.zeros(max(R, 1), dtype=torch.int32, device=dev), ranges=torch.zeros(T, 2, dtype=torch.int32, device=dev),
+             n_contrib=torch.zeros(W * H, dtype=torch.int32, device=dev), final_T=torch.zeros(W * H, device=dev))
+    _lib.check(L.psb_debug_export(P, R, W, H, geom.data_ptr(), binning.data_ptr() if R else None, img.data_ptr(),
+                                  o["depths"].data_ptr(), o["means2D"].data_ptr(), o["conic_opacity"].data_ptr(), o["rgb"].data_ptr(),
+                                  o["clamped"].data_ptr(), o["tiles_touched"].data_ptr(), o["keys_sorted"].data_ptr(),
+                                  o["values_sorted"].data_ptr(), o["ranges"].data_ptr(), o["n_contrib"].data_ptr(),
+                                  o["final_T"].data_ptr(), None), "psb_debug_export")
+    torch.cuda.synchronize()
+    o["keys_sorted"], o["values_sorted"] = o["keys_sorted"][:R], o["values_sorted"][:R]
+    return o
+
+
+def _compare_forward(mine, ref, P, W, H, label):
+    _, ref_gpu = _mods()
+    nr_m, col_m, rad_m, gb_m, bb_m, ib_m = mine
+    nr_r, col_r, rad_r, gb_r, bb_r, ib_r = ref
+    assert nr_m == nr_r, f"{label}: num_rendered {nr_m} != {nr_r}"
+    nbad = (rad_m != rad_r).sum().item()
+    assert nbad == 0, f"{label}: {nbad}/{P} radii differ"
+    m = _export_mine(P, nr_m, W, H, gb_m, bb_m, ib_m)
+    r = ref_gpu.intermediates(P, nr_r, W, H, gb_r, bb_r, ib_r)
+    vis = rad_r > 0
+    assert torch.equal(m["tiles_touched"], r["tiles_touched"]), f"{label}: tiles_touched differ"
+    report = {}
+    for k in ("depths", "means2D", "conic_opacity", "rgb"):
+        a, b = m[k][vis], r[k][vis]
+        report[k] = (a != b).double().mean().item() if a.numel() else 0.0
+        assert rel_close(a, b) == 0.0, f"{label}: {k} outside 1e-4 relative"
+    assert torch.equal(m["depths"][vis], r["depths"][vis]), f"{label}: depth bits differ ({report['depths']:.2e} of entries)"
+    assert torch.equal(m["means2D"][vis], r["means2D"][vis]), f"{label}: pixel centres differ"
+    assert torch.equal(m["clamped"][vis].bool(), r["clamped"][vis].bool()), f"{label}: clamp flags differ"
+    if nr_m:
+        assert torch.equal(m["keys_sorted"], r["keys_sorted"]), f"{label}: sorted (tile|depth) keys differ"
+        assert torch.equal(m["values_sorted"], r["values_sorted"]), f"{label}: sorted Gaussian ids differ"
+    assert torch.equal(m["ranges"], r["ranges"]), f"{label}: tile ranges differ"
+    nc_bad = (m["n_contrib"] != r["n_contrib"]).sum().item()
+    assert nc_bad == 0, f"{label}: n_contrib differs on {nc_bad} pixels"
+    assert rel_close(m["final_T"], r["final_T"]) == 0.0, f"{label}: final_T"
+    assert rel_close(col_m, col_r, atol=1e-6) == 0.0, f"{label}: out_color"
+    report["final_T_bitdiff"] = (m["final_T"] != r["final_T"]).double().mean().item()
+    report["color_bitdiff"] = (col_m != col_r).double().mean().item()
+    return report
+
+
+CONFIGS = [
+    # (P, camera, wh, pose_seed, D, bg, scale_px)
+    (50_000, "tum", None, 3, 3, (0.0, 0.0, 0.0), 2.4),
+    (200_000, "replica", None, None, 3, (0.0, 0.0, 0.0), 2.4),
+    (20_000, "euroc", None, 5, 2, (0.2, 0.5, 0.7), 4.0),
+    (5_000, "tum", (203, 117), 7, 1, (1.0, 1.0, 1.0), 6.0),
+    (3_000, "tum", (64, 48), 9, 0, (0.0, 0.0, 0.0), 12.0),
+]
+
+
+@pytest.mark.parametrize("P,camname,wh,pose_seed,D,bg,scale_px", CONFIGS)
+def test_forward_matches_reference(cuda, P, camname, wh, pose_seed, D, bg, scale_px):
+    cam, sc, act, g, c = scene_tensors(P, camname, seed=P % 97, pose_seed=pose_seed, dev=cuda, wh=wh, scale_px=scale_px)
+    bgt = torch.tensor(bg, dtype=torch.float32, device=cuda)
+    mine, ref, _ = _run_both(g, c, D, bgt)
+    rep = _compare_forward(mine, ref, P, c["W"], c["H"], f"P={P} {camname}")
+    print("bitwise-different fractions:", rep, "num_rendered", mine[0])
+
+
+def _grads_both(g, c, D, bgt, mine, ref, extra, dL):
+    rasterizer, ref_gpu = _mods()
+    sh, col, sca, rot, cov = extra
+    common = lambda rad: (bgt, g["means3D"], rad, col, sca, rot, 1.0, cov, c["viewmatrix"], c["projmatrix"], c["tanfovx"],
+                          c["tanfovy"], dL, sh, D, c["campos"])
+    gm = rasterizer.RasterizeGaussiansBackwardCUDA(*common(mine[2]), mine[3], mine[0], mine[4], mine[5])
+    gr = ref_gpu.rasterize_backward(*common(ref[2]), ref[3], ref[0], ref[4], ref[5])
+    torch.cuda.synchronize()
+    return gm, gr
+
+
+NAMES = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations"]
+
+
+def _loss_grad(color, gt):
+    """dL/dcolor of the reference's training loss (L1 + 0.2 DSSIM), via torch autograd on the GPU."""
+    import torch.nn.functional as F
+    x = color.detach().clone().requires_grad_(True)
+    win1 = torch.tensor([np.exp(-(i - 5) ** 2 / (2 * 1.5 ** 2)) for i in range(11)], dtype=torch.float32, device=x.device)
+    win1 = (win1 / win1.sum()).unsqueeze(1)
+    win = (win1 @ win1.t()).expand(3, 1, 11, 11).contiguous()
+    a, b = x.unsqueeze(0), gt.unsqueeze(0)
+    mu1, mu2 = F.conv2d(a, win, padding=5, groups=3), F.conv2d(b, win, padding=5, groups=3)
+    s1 = F.conv2d(a * a, win, padding=5, groups=3) - mu1 ** 2
+    s2 = F.conv2d(b * b, win, padding=5, groups=3) - mu2 ** 2
+    s12 = F.conv2d(a * b, win, padding=5, groups=3) - mu1 * mu2
+    ssim = (((2 * mu1 * mu2 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1 ** 2 + mu2 ** 2 + 1e-4) * (s1 + s2 + 9e-4))).mean()
+    loss = 0.8 * (x - gt).abs().mean() + 0.2 * (1 - ssim)
+    loss.backward()
+    return x.grad.contiguous()
+
+
+@pytest.mark.parametrize("P,camname,wh,pose_seed,D,bg,scale_px", CONFIGS)
+def test_backward_matches_reference(cuda, P, camname, wh, pose_seed, D, bg, scale_px):
+    cam, sc, act, g, c = scene_tensors(P, camname, seed=P % 97, pose_seed=pose_seed, dev=cuda, wh=wh, scale_px=scale_px)
+    bgt = torch.tensor(bg, dtype=torch.float32, device=cuda)
+    mine, ref, extra = _run_both(g, c, D, bgt)
+    gt = torch.rand((3, c["H"], c["W"]), device=cuda, generator=torch.Generator(device=cuda).manual_seed(1))
+    dL = _loss_grad(ref[1], gt)
+    gm, gr = _grads_both(g, c, D, bgt, mine, ref, extra, dL)
+    vis = ref[2] > 0
+    # run the (atomics-ordered, non-deterministic) reference a second time: its own run-to-run spread is the floor
+    _, gr2 = _grads_both(g, c, D, bgt, mine, ref, extra, dL)
+    for name, a, b, b2 in zip(NAMES, gm, gr, gr2):
+        scale = b.abs().max().item() + 1e-30
+        frac = rel_close(a[vis], b[vis], rtol=1e-4, atol=1e-6 * scale)
+        self_frac = rel_close(b2[vis], b[vis], rtol=1e-4, atol=1e-6 * scale)
+        nrm = ((a - b).double().norm() / (b.double().norm() + 1e-30)).item()
+        print(f"{name}: frac>1e-4 mine-vs-ref {frac:.2e} (ref-vs-ref {self_frac:.2e}), rel-norm err {nrm:.2e}")
+        assert nrm < 2e-5, f"{name}: relative norm error {nrm}"
+        assert frac <= max(5e-4, 3 * self_frac), f"{name}: {frac} of visible entries outside 1e-4 (reference vs itself: {self_frac})"
+        assert torch.equal(a[~vis], torch.zeros_like(a[~vis])), f"{name}: rows of invisible Gaussians must stay zero"
+
+
+def test_precomputed_colour_and_covariance(cuda):
+    P, D = 30_000, 3
+    cam, sc, act, g, c = scene_tensors(P, "tum", seed=11, pose_seed=2, dev=cuda)
+    bgt = torch.tensor((0.1, 0.2, 0.3), device=cuda)
+    mine0, ref0, _ = _run_both(g, c, D, bgt)
+    _, ref_gpu = _mods()
+    inter = ref_gpu.intermediates(P, ref0[0], c["W"], c["H"], ref0[3], ref0[4], ref0[5])
+    colors = torch.rand((P, 3), device=cuda)
+    cov3D = inter["cov3D"].clone()
+    cov3D[ref0[2] <= 0] = 0  # rows never written by the reference
+    mine, ref, extra = _run_both(g, c, D, bgt, colors=colors, cov3D=cov3D)
+    _compare_forward(mine, ref, P, c["W"], c["H"], "precomp")
+    dL = torch.randn((3, c["H"], c["W"]), device=cuda) / (3 * c["H"] * c["W"])
+    gm, gr = _grads_both(g, c, D, bgt, mine, ref, extra, dL)
+    for name, a, b in zip(NAMES, gm, gr):
+        if a.numel() == 0:
+            continue
+        nrm = ((a - b).double().norm() / (b.double().norm() + 1e-30)).item()
+        assert nrm < 2e-5, f"{name}: {nrm}"
+
+
+def test_edge_cases(cuda):
+    rasterizer, ref_gpu = _mods()
+    # all culled, single Gaussian, one huge Gaussian covering every tile, image smaller than a tile
+    for P, wh, scale_px, zshift in [(64, (40, 24), 2.0, -100.0), (1, (96, 64), 30.0, 0.0), (7, (96, 64), 400.0, 0.0), (100, (9, 5), 3.0, 0.0)]:
+        cam, sc, act, g, c = scene_tensors(P, "tum", seed=5, pose_seed=None, dev=cuda, wh=wh, scale_px=scale_px)
+        g["means3D"] = g["means3D"].clone()
+        g["means3D"][:, 2] += zshift
+        bgt = torch.tensor((0.3, 0.1, 0.6), device=cuda)
+        mine, ref, extra = _run_both(g, c, 3, bgt)
+        _compare_forward(mine, ref, P, c["W"], c["H"], f"edge P={P} wh={wh}")
+        dL = torch.ones((3, c["H"], c["W"]), device=cuda)
+        gm, gr = _grads_both(g, c, 3, bgt, mine, ref, extra, dL)
+        for name, a, b in zip(NAMES, gm, gr):
+            assert rel_close(a, b, rtol=2e-4, atol=1e-5 * (b.abs().max().item() + 1e-30)) <= 0.01, f"{name} P={P}"
+    # P == 0 short-circuit (reference rasterize_points.cu:81,159)
+    e = torch.empty(0, device=cuda)
+    out = rasterizer.RasterizeGaussiansCUDA(torch.zeros(3, device=cuda), torch.zeros((0, 3), device=cuda), e, e, e, e, 1.0, e,
+                                            torch.eye(4, device=cuda).flatten(), torch.eye(4, device=cuda).flatten(), 1.0, 1.0, 32, 32,
+                                            torch.zeros((0, 16, 3), device=cuda), 3, torch.zeros(3, device=cuda), False)
+    assert out[0] == 0 and out[1].abs().sum().item() == 0
+    with pytest.raises(RuntimeError):
+        rasterizer.RasterizeGaussiansCUDA(torch.zeros(3, device=cuda), torch.zeros((4, 2), device=cuda), e, e, e, e, 1.0, e, e, e, 1.0,
+                                          1.0, 32, 32, e, 3, e, False)
+
+
+def test_mark_visible(cuda):
+    rasterizer, ref_gpu = _mods()
+    cam, sc, act, g, c = scene_tensors(10_000, "tum", seed=3, pose_seed=4, dev=cuda)
+    a = rasterizer.markVisible(g["means3D"], c["viewmatrix"], c["projmatrix"])
+    b = ref_gpu.mark_visible(g["means3D"], c["viewmatrix"], c["projmatrix"])
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("n,nbits", [(1, 32), (31, 6), (4095, 12), (4096, 32), (4097, 9), (100_000, 12), (1_000_003, 32), (3_000_000, 17)])
+def test_radix_sort_pairs(cuda, n, nbits):
+    from photo_slam_b200 import _lib
+    L = _lib.lib()
+    gen = torch.Generator(device=cuda).manual_seed(n)
+    hi = (1 << nbits) if nbits < 31 else (1 << 31) - 1
+    keys = torch.randint(0, hi, (n,), device=cuda, dtype=torch.int64, generator=gen)
+    if nbits == 32:
+        keys = keys * 2 + torch.randint(0, 2, (n,), device=cuda, generator=gen)
+    vals = torch.arange(n, device=cuda, dtype=torch.int32)
+    k32 = keys.to(torch.int64).bitwise_and(0xFFFFFFFF)
+    kk = k32.clone()
+    kk[kk >= 2 ** 31] -= 2 ** 32
+    kdev = kk.to(torch.int32).contiguous()
+    vdev = vals.clone()
+    _lib.check(L.psb_debug_sort_pairs(kdev.data_ptr(), vdev.data_ptr(), n, nbits, None), "sort")
+    torch.cuda.synchronize()
+    order = torch.sort(k32, stable=True).indices.to(torch.int32)
+    assert torch.equal(vdev, order)
+
+
+def test_autograd_wrapper_matches_reference_chain(cuda):
+    """GaussianRasterizer (autograd) end to end: same gradients on the leaf tensors as the reference chain."""
+    rasterizer, ref_gpu = _mods()
+    P, D = 20_000, 3
+    cam, sc, act, g, c = scene_tensors(P, "tum", seed=21, pose_seed=6, dev=cuda)
+    bgt = torch.zeros(3, device=cuda)
+    leaves = {k: g[k].clone().requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    rs = rasterizer.GaussianRasterizationSettings(c["H"], c["W"], c["tanfovx"], c["tanfovy"], bgt, 1.0, c["viewmatrix"],
+                                                  c["projmatrix"], D, c["campos"], False)
+    color, radii = rasterizer.GaussianRasterizer(rs)(leaves["means3D"], means2D, leaves["opacities"], shs=leaves["shs"],
+                                                     scales=leaves["scales"], rotations=leaves["rotations"])
+    w = torch.randn_like(color)
+    (color * w).sum().backward()
+    mine, ref, extra = _run_both(g, c, D, bgt)
+    gm, gr = _grads_both(g, c, D, bgt, mine, ref, extra, w)
+    pairs = [(means2D.grad, gr[0]), (leaves["opacities"].grad, gr[2]), (leaves["means3D"].grad, gr[3]), (leaves["shs"].grad, gr[5]),
+             (leaves["scales"].grad, gr[6]), (leaves["rotations"].grad, gr[7])]
+    for a, b in pairs:
+        assert ((a - b).double().norm() / (b.double().norm() + 1e-30)).item() < 2e-5
+    assert torch.equal(radii, ref[2])
+    with pytest.raises(RuntimeError):
+        rasterizer.GaussianRasterizer(rs)(leaves["means3D"], means2D, leaves["opacities"], shs=leaves["shs"],
+                                          colors_precomp=torch.rand((P, 3), device=cuda), scales=leaves["scales"],
+                                          rotations=leaves["rotations"])
