@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — train iters/s (+ render Mpix/s, per-kernel HBM roofline) of the Gaussian-splatting hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl psb|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[3], the configuration north_star quotes its target on; fits one GPU):
+synthetic 3 M Gaussians (SURVEY.md §8(d) distribution, seed 0), 1200x680 Replica intrinsics, SH degree 3,
+one training iteration = render -> L1 + 0.2 DSSIM -> backward -> densification statistics -> Adam over all
+59 floats/Gaussian. N > 1: the scene is replicated, rank r trains on its own view, ONE NCCL all-reduce of the
+[P,59] gradient per step (weak scaling; value = views/s over all ranks).
+
+--impl psb        this repository's sm_100a path through its C-ABI (photo_slam_b200.trainer)
+--impl reference  the reference's own cuda_rasterizer kernels (oracle/_ref, compiled unmodified for sm_100a) inside
+                  the reference's iteration restated with the same ATen ops LibTorch runs (oracle/ref_trainer.py).
+                  The reference has NO CPU implementation of this path; this is its real code path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+
+import photo_slam_b200.synthetic as syn  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="psb", choices=["psb", "reference"])
+    ap.add_argument("--points", type=int, default=3_000_000)
+    ap.add_argument("--camera", default="replica")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop = index, [], False
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.samples.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(self.samples)}
+
+
+def dist_setup(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms, world, dev):
+    if world == 1:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
+def make_inputs(args, rank, dev):
+    W, H, fx, fy = syn.CAMERAS[args.camera]
+    cam0 = syn.make_camera(W, H, fx, fy)                     # scene is laid out in front of the identity view
+    scene = syn.make_scene(args.points, cam0, seed=0)
+    if rank == 0:
+        cam = cam0
+    else:                                                    # every rank trains on its own keyframe
+        R, t = syn.random_pose(np.random.default_rng(100 + rank), max_angle=0.05, max_trans=0.1)
+        cam = syn.make_camera(W, H, fx, fy, R, t)
+    gt = syn.target_image(H, W, seed=1 + rank)
+    host = dict(gt=torch.from_numpy(gt).pin_memory(), viewmatrix=torch.from_numpy(cam["viewmatrix"]).pin_memory(),
+                projmatrix=torch.from_numpy(cam["projmatrix"]).pin_memory(), campos=torch.from_numpy(cam["campos"]).pin_memory())
+    devcam = dict(viewmatrix=host["viewmatrix"].to(dev), projmatrix=host["projmatrix"].to(dev), campos=host["campos"].to(dev),
+                  tanfovx=float(cam["tanfovx"]), tanfovy=float(cam["tanfovy"]), W=W, H=H)
+    return scene, cam, host, devcam, host["gt"].to(dev)
+
+
+def cpu_baseline():
+    """CPU restatement (oracle port, OpenMP) on a bounded sample: config A, forward + backward, no Adam."""
+    import oracle_c
+    W, H, fx, fy = syn.CAMERAS["tum"]
+    cam = syn.make_camera(W, H, fx, fy)
+    act = syn.activate(syn.make_scene(50_000, cam, seed=0))
+    dL = (np.random.default_rng(0).normal(size=(3, H, W)) / (3 * H * W)).astype(np.float32)
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    f = oracle_c.forward(cam, act)          # warm-up (page-in, thread pool)
+    n, t0 = 0, time.time()
+    while n < 3 or (time.time() - t0 < 10 and n < 40):
+        f = oracle_c.forward(cam, act)
+        oracle_c.backward(cam, act, f, dL)
+        n += 1
+    dt = (time.time() - t0) / n
+    return {"value": 1.0 / dt, "unit": "iters/s", "cores": cores, "kind": "port",
+            "sample": f"config A (50k Gaussians, 640x480): {n} x (forward + backward) of oracle/gs_oracle.c, OpenMP on the per-Gaussian and forward-blend loops; no loss/Adam"}
+
+
+def algorithmic_bytes(P, P_vis, N, W, H, T):
+    """SURVEY.md §8(d) per-unit figures x units of this workload, per stage of psb_trainer_step (bytes)."""
+    return {
+        "preprocess": 236 * P + 75 * P_vis + 8 * P,
+        "depth_sort_scan": 4 * 16 * P + 8 * P,                 # 4 onesweep passes over (key,value) + offsets scan
+        "binning": 20 * P_vis + 8 * N + 2 * 16 * N + 4 * N + 8 * T,  # emit + 2 tile-sort passes + ranges
+        "render_fwd": 4 * N + 48 * N + 20 * W * H + 8 * T,        # upper bound: whole list consumed
+        "loss": (2 * 12 + 12) * W * H + 2 * 36 * W * H,
+        "render_bwd": 4 * N + 48 * N + 20 * W * H + 36 * P_vis,
+        "backward_adam": 1652 * P + 48 * P_vis + 96 * P,          # 28 B x 59 params + screen-space sums read + sink re-zero
+    }
+
+
+def run_psb(args, world, rank, local, dev):
+    from photo_slam_b200 import trainer as T
+    scene, cam, host, devcam, gt_dev = make_inputs(args, rank, dev)
+    model = T.GaussianModel.from_numpy(scene, dev)
+    model.trainingSetup(T.GaussianOptimizationParams())
+    tr = T.DataParallelTrainer(model) if world > 1 else T.GaussianTrainer(model)
+    P, W, H = args.points, devcam["W"], devcam["H"]
+    radii = torch.zeros(P, dtype=torch.int32, device=dev)
+
+    # --- warm-up (also grows the binning arena if needed)
+    for _ in range(max(args.warmup, 3)):
+        tr.trainForOneIteration(devcam, gt_dev, radii=radii)
+        loss0, _, _, n_inst = tr.result()
+    P_vis = int((radii > 0).sum().item())
+
+    # --- value: K iterations, inputs resident in HBM, no host sync inside (parameters + moments = 2.1 GB >> L2)
+    barrier(world)
+    with ClockSampler(local) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            tr.trainForOneIteration(devcam, gt_dev)
+        e1.record()
+        barrier(world)
+        ms_total = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    tr.result()
+    clocks = clk.summary()
+    ms_step = ms_total / args.steps
+
+    # --- e2e: the call a user makes, host buffers in, loss out, every step
+    stage = dict(gt=torch.empty_like(gt_dev), viewmatrix=torch.empty_like(devcam["viewmatrix"]), projmatrix=torch.empty_like(devcam["projmatrix"]),
+                 campos=torch.empty_like(devcam["campos"]))
+    cam2 = dict(devcam, viewmatrix=stage["viewmatrix"], projmatrix=stage["projmatrix"], campos=stage["campos"])
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        for k in ("gt", "viewmatrix", "projmatrix", "campos"):
+            stage[k].copy_(host[k], non_blocking=True)
+        tr.trainForOneIteration(cam2, stage["gt"])
+        loss_host = tr.result()[0]          # device -> host read of the step's loss (blocks, like loss.item())
+    e1.record()
+    barrier(world)
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1), world, dev) / args.steps
+    h2d = sum(host[k].numel() * 4 for k in ("gt", "viewmatrix", "projmatrix", "campos"))
+
+    # --- forward-only render throughput and per-stage roofline (separate, untimed-for-value passes)
+    img = torch.empty((3, H, W), device=dev)
+    for _ in range(3):
+        tr.render(devcam, img)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        tr.render(devcam, img)
+    e1.record()
+    torch.cuda.synchronize()
+    render_ms = e0.elapsed_time(e1) / 10
+    stages, roof, stage_table = None, None, None
+    if world == 1:
+        tr.set_profiling(True)
+        acc = {}
+        for _ in range(5):
+            tr.trainForOneIteration(devcam, gt_dev)
+            tr.result()
+            for k, v in tr.stage_times().items():
+                acc.setdefault(k, []).append(v)
+        tr.set_profiling(False)
+        stages = {k: float(np.median(v)) for k, v in acc.items()}
+        T_tiles = ((W + 15) // 16) * ((H + 15) // 16)
+        ab = algorithmic_bytes(P, P_vis, n_inst, W, H, T_tiles)
+        peak = 6650.0
+        peak_src = "fallback"
+        try:
+            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            peak_src = "measured"
+        except Exception:
+            pass
+        stage_table = {k: {"ms": stages[k], "alg_GB": ab[k] / 1e9, "GBps": ab[k] / 1e6 / stages[k], "frac_of_hbm_peak": ab[k] / 1e6 / stages[k] / peak}
+                       for k in stages}
+        top = max(stages, key=stages.get)
+        roof = {"kernel": top, "bound": "hbm", "achieved": stage_table[top]["GBps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": stage_table[top]["frac_of_hbm_peak"], "traffic": None,
+                "note": "achieved = SURVEY §8(d) algorithmic bytes of the stage / its CUDA-event time inside psb_trainer_step; see stages for every stage"}
+
+    launches_per_step = 19 if world == 1 else 25  # kernels of this library per iteration (memsets not counted)
+    out = {
+        "metric": "train_iters_per_sec", "value": world * 1000.0 / ms_step, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "impl": "psb",
+        "config": {"workload": f"D: synthetic {P} Gaussians (SURVEY 8d, seed 0), {W}x{H} {args.camera} intrinsics, SH degree 3, 1 view/GPU/step, "
+                               "render + L1+0.2DSSIM + backward + densify stats + Adam(59 floats/Gaussian)",
+                   "gaussians": P, "visible": P_vis, "num_rendered": n_inst, "width": W, "height": H,
+                   "l2_policy": "working set (2.1 GB of parameters + moments per step) is larger than L2; no explicit flush",
+                   "parallelism": "single GPU" if world == 1 else f"replicated scene, keyframe-sharded, NCCL all-reduce of [P,59] gradients x{world}"},
+        "e2e": {"value": world * 1000.0 / ms_e2e, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 20},
+        "render_mpix_per_s": W * H / 1e6 / (render_ms / 1e3), "render_ms": render_ms,
+        "gpu_launches": launches_per_step * args.steps, "loss": loss_host, "clocks": clocks,
+    }
+    if stage_table:
+        out["stages"] = stage_table
+        out["roofline"] = roof
+    return out
+
+
+def run_reference(args, dev):
+    import ref_gpu
+    if not ref_gpu.available():
+        return {"impl": "reference", "unavailable": "oracle/_ref/libref_rasterizer.so not built (needs /root/reference at build time)"}
+    import ref_trainer
+    scene, cam, host, devcam, gt_dev = make_inputs(args, 0, dev)
+    lrs = [0.00032, 0.0025, 0.0025 / 20, 0.05, 0.005, 0.001]
+    ref = ref_trainer.RefTrainer(scene, dev, lrs)
+    P, W, H = args.points, devcam["W"], devcam["H"]
+    for _ in range(max(args.warmup, 3)):
+        loss, _, radii = ref.train_for_one_iteration(devcam, gt_dev)
+    P_vis = int((radii > 0).sum().item())
+    torch.cuda.synchronize()
+    with ClockSampler(torch.cuda.current_device()) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            ref.train_for_one_iteration(devcam, gt_dev, sync=False)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_step = e0.elapsed_time(e1) / args.steps
+    clocks = clk.summary()
+    # e2e exactly as the reference does it: gt_image = original_image_.cuda() every iteration, cuda::synchronize, loss.item()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        gt = host["gt"].to(dev, non_blocking=True)
+        cam2 = dict(devcam, viewmatrix=host["viewmatrix"].to(dev, non_blocking=True), projmatrix=host["projmatrix"].to(dev, non_blocking=True),
+                    campos=host["campos"].to(dev, non_blocking=True))
+        loss, _, _ = ref.train_for_one_iteration(cam2, gt, sync=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    h2d = sum(host[k].numel() * 4 for k in ("gt", "viewmatrix", "projmatrix", "campos"))
+    with torch.no_grad():
+        for _ in range(3):
+            ref.render(devcam)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ref.render(devcam)
+        e1.record()
+        torch.cuda.synchronize()
+        render_ms = e0.elapsed_time(e1) / 10
+    val = 1000.0 / ms_step
+    return {
+        "metric": "train_iters_per_sec", "value": val, "unit": "iters/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "impl": "reference",
+        "config": {"workload": f"D: synthetic {P} Gaussians (SURVEY 8d, seed 0), {W}x{H} {args.camera} intrinsics, SH degree 3, 1 view/step, "
+                               "render + L1+0.2DSSIM + backward + densify stats + Adam(59 floats/Gaussian)",
+                   "gaussians": P, "visible": P_vis, "width": W, "height": H,
+                   "reference_path": "reference cuda_rasterizer kernels (unmodified, sm_100a) + ATen ops of the reference's LibTorch host loop, on the GPU"},
+        "cpu_baseline": {"value": val, "unit": "iters/s", "cores": 0, "kind": "reference",
+                         "sample": "the reference has no CPU implementation of this path; this arm is its CUDA path on the same B200 (whole workload, not a sample)"},
+        "e2e": {"value": 1000.0 / ms_e2e, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "render_mpix_per_s": W * H / 1e6 / (render_ms / 1e3), "render_ms": render_ms, "loss": float(loss), "clocks": clocks,
+    }
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        # rank 0 alone runs the reference arm; the other ranks of a torchrun launch exit without work
+        if int(os.environ.get("RANK", "0")) == 0:
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+            print(json.dumps(run_reference(args, torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))), flush=True)
+        return
+    world, rank, local = dist_setup(args)
+    dev = torch.device("cuda", local)
+    out = run_psb(args, world, rank, local, dev)
+    if rank == 0:
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

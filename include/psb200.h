@@ -100,6 +100,92 @@ int psb_debug_export(int P, int R, int width, int height,
                      uint32_t* tiles_touched, uint64_t* keys_sorted, uint32_t* values_sorted,
                      uint32_t* ranges, uint32_t* n_contrib, float* final_T, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Trainer-level surface: one fused training iteration on the RAW model tensors.
+ *
+ * Replaces the body of GaussianMapper::trainForOneIteration (src/gaussian_mapper.cpp:677-772) /
+ * GaussianTrainer::trainingOnce (src/gaussian_trainer.cpp:31-135) between "pick a keyframe" and
+ * "densify": GaussianRenderer::render (src/gaussian_renderer.cpp:23-149) incl. the activations of
+ * src/gaussian_model.cpp:48-71, loss_utils::l1_loss / ssim (include/loss_utils.h:28-124), loss.backward(),
+ * max_radii2D / addDensificationStats (gaussian_mapper.cpp:714-719, gaussian_model.cpp:817-831) and
+ * gaussians_->optimizer_->step() + zero_grad (torch::optim::Adam over the 6 groups of
+ * gaussian_model.cpp:477-503). Tensor layouts are the reference's (include/gaussian_model.h):
+ *   index 0 xyz [P,3] | 1 features_dc [P,1,3] | 2 features_rest [P,15,3] | 3 opacity [P,1] (logit) |
+ *   4 scaling [P,3] (log) | 5 rotation [P,4] (w,x,y,z, unnormalised);   all device float32, contiguous.
+ * ------------------------------------------------------------------------------------------------ */
+#define PSB_ERR_RETRY (-4)
+
+typedef struct psb_trainer psb_trainer; /* opaque: scratch arena of the iteration */
+
+typedef struct psb_model {
+	float* param[6];          /* parameters, updated in place by psb_trainer_step / psb_adam_update */
+	float* exp_avg[6];        /* Adam first moments  (same shapes) */
+	float* exp_avg_sq[6];     /* Adam second moments (same shapes) */
+	float* max_radii2D;       /* [P]   or NULL */
+	float* xyz_gradient_accum;/* [P,1] or NULL */
+	float* denom;             /* [P,1] or NULL */
+} psb_model;
+
+typedef struct psb_camera {
+	const float* viewmatrix;  /* device, 16 floats, column-major (world_view_transform_ memory) */
+	const float* projmatrix;  /* device, 16 floats (full_proj_transform_ memory) */
+	const float* campos;      /* device, 3 floats */
+	float tan_fovx, tan_fovy;
+	int width, height;
+} psb_camera;
+
+typedef struct psb_step {
+	float lr[6];              /* per-group learning rates, order as psb_model.param */
+	float beta1, beta2, eps;  /* reference: 0.9, 0.999, 1e-15 (gaussian_model.cpp:483-485) */
+	int step;                 /* 1-based Adam step count of THIS update */
+	float lambda_dssim;       /* reference default 0.2 */
+	int sh_degree;            /* active SH degree 0..3 */
+	int update_densify_stats; /* != 0: fold max_radii2D / xyz_gradient_accum / denom updates in */
+} psb_step;
+
+int psb_trainer_create(psb_trainer** out);
+int psb_trainer_destroy(psb_trainer* t);
+
+/* Forward only, from raw parameters (GaussianMapper::renderFromPose, gaussian_mapper.cpp:1521-1569).
+ * out_color [3,H,W] device; radii [P] int32 device or NULL. M must be 16. Asynchronous on `stream`. */
+int psb_trainer_render(psb_trainer* t, int P, int M, const psb_model* model, const psb_camera* camera,
+                       const float* background, int sh_degree, float* out_color, int* radii, void* stream);
+
+/* One fused iteration: render -> loss -> backward -> Adam (parameters and moments updated in place).
+ * gt_image [3,H,W] device; mask [3,H,W] device or NULL (undistortion mask, gaussian_mapper.cpp:692);
+ * out_color / radii optional outputs. Asynchronous: no host synchronisation happens inside. */
+int psb_trainer_step(psb_trainer* t, int P, int M, const psb_model* model, const psb_camera* camera,
+                     const float* background, const float* gt_image, const float* mask, const psb_step* step,
+                     float* out_color, int* radii, void* stream);
+
+/* Data-parallel halves of the same iteration: psb_trainer_backward writes the gradients w.r.t. the RAW
+ * parameters into grads[0..5] (shapes of psb_model.param; every row written, zeros for invisible Gaussians)
+ * and updates the densification statistics but NOT the parameters; after the all-reduce of `grads`,
+ * psb_adam_update applies torch::optim::Adam semantics with g = grads * grad_scale. */
+int psb_trainer_backward(psb_trainer* t, int P, int M, const psb_model* model, const psb_camera* camera,
+                         const float* background, const float* gt_image, const float* mask, const psb_step* step,
+                         float* out_color, int* radii, float* const* grads, void* stream);
+int psb_adam_update(int P, int M, const psb_model* model, float* const* grads, const psb_step* step,
+                    float grad_scale, void* stream);
+
+/* Blocks on `stream` and returns the results of the last step / backward / render:
+ * out3 = {loss, l1, ssim} (host, may be NULL), *num_rendered (may be NULL).
+ * Returns PSB_ERR_RETRY when the binning arena was too small for that view: the step was a no-op on the
+ * model, the arena has been grown, call the step again. */
+int psb_trainer_result(psb_trainer* t, float* out3, int* num_rendered, void* stream);
+
+/* Optional per-stage timing of psb_trainer_step with CUDA events recorded on the step's stream (bench.py uses
+ * it for the roofline numbers; off by default). ms[0..6] = preprocess, depth sort + scan, binning (emit + tile
+ * sort + ranges), render forward, loss forward+backward, render backward, fused per-Gaussian backward + Adam. */
+int psb_trainer_set_profiling(psb_trainer* t, int enable);
+int psb_trainer_stage_times(psb_trainer* t, float* ms, int n);
+
+/* Stand-alone fused loss (tests / evaluation): L = (1-lambda) L1 + lambda (1 - SSIM), reference
+ * include/loss_utils.h:28-124. image/gt/mask/dL_dimage device [3,H,W] (mask, dL_dimage may be NULL);
+ * out3_host = {loss, l1, ssim}. Synchronises the stream. */
+int psb_loss(int height, int width, const float* image, const float* gt_image, const float* mask,
+             float lambda_dssim, float* dL_dimage, float* out3_host, void* stream);
+
 /* Standalone sort primitive (tests): stable LSD radix sort of (u32 key, u32 value) pairs on key bits
  * [0, nbits). keys/vals are device arrays of n elements, sorted in place. */
 int psb_debug_sort_pairs(uint32_t* keys, uint32_t* vals, size_t n, int nbits, void* stream);

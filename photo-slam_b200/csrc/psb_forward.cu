@@ -208,8 +208,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(int P, const
 __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint2* __restrict__ rect,
                                                              const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ offsets,
                                                              uint32_t* __restrict__ tile_key, uint32_t* __restrict__ inst, int grid_x,
-                                                             uint32_t capacity)
+                                                             uint32_t capacity, const uint32_t* __restrict__ n_dev)
 {
+	if (n_dev && *n_dev > capacity) return;  // arena too small for this view: emit nothing (the step becomes a no-op)
 	const int j = blockIdx.x * blockDim.x + threadIdx.x;
 	const int lane = threadIdx.x & 31;
 	uint32_t g = 0, tt = 0, off = 0, x0 = 0, y0 = 0, w = 1;
@@ -221,7 +222,6 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32
 			x0 = r.x & 0xFFFFu; y0 = r.x >> 16;
 			w = (r.y & 0xFFFFu) - x0;
 			off = offsets[j];
-			if (off + tt > capacity) tt = 0;  // cannot happen when capacity >= num_rendered; guards the arena mode
 		}
 	}
 	constexpr uint32_t SMALL = 6;
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32
 __global__ void tile_ranges_kernel(const uint32_t* __restrict__ n_dev, uint32_t n_host, const uint32_t* __restrict__ tile_key_sorted,
                                    uint2* __restrict__ ranges)
 {
-	const uint32_t n = n_dev ? min(*n_dev, n_host) : n_host;
+	const uint32_t n = n_dev ? (*n_dev > n_host ? 0u : *n_dev) : n_host;
 	const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= n) return;
 	const uint32_t cur = tile_key_sorted[idx];
@@ -316,7 +316,7 @@ int launch_binning(int P, const Camera& cam, const GeomState& geom, BinState& bi
 	PSB_CUDA_OK(cudaMemsetAsync(img.ranges, 0, (size_t)num_tiles * sizeof(uint2), stream));
 	if (P == 0 || n_host == 0) return 0;
 	emit_instances_kernel<<<cdiv(P, 256), 256, 0, stream>>>(P, geom.order[0], geom.rect, geom.tiles_touched, geom.offsets, bin.tile_key[0],
-	                                                       bin.inst[0], cam.grid_x, (uint32_t)n_host);
+	                                                       bin.inst[0], cam.grid_x, (uint32_t)n_host, n_dev);
 	PSB_LAUNCH_OK();
 	const SortPlan plan = make_sort_plan(tile_id_bits(num_tiles));
 	int rc = radix_sort_pairs(bin.tile_key, bin.inst, false, n_dev, n_host, plan, bin.sort_scratch, bin.sort_scratch_bytes, stream);

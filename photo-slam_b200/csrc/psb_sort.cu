@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) rs_histogram_kernel(const uint32_t* __res
                                                            uint32_t n_host, SortPlan plan, uint32_t* __restrict__ hist)
 {
 	__shared__ uint32_t sh[RS_MAX_PASS][RS_RADIX];
-	const uint32_t n = n_dev ? min(*n_dev, n_host) : n_host;
+	const uint32_t n = n_dev ? (*n_dev > n_host ? 0u : *n_dev) : n_host;  // overflowed arena: sort nothing
 	for (int i = threadIdx.x; i < RS_MAX_PASS * RS_RADIX; i += blockDim.x) (&sh[0][0])[i] = 0;
 	__syncthreads();
 	const uint32_t stride = gridDim.x * blockDim.x * 4;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint32_t*
 	__shared__ uint32_t s_warp_tot[RS_THREADS / 32];
 	__shared__ uint32_t s_tile;
 
-	const uint32_t n = n_dev ? min(*n_dev, n_host) : n_host;
+	const uint32_t n = n_dev ? (*n_dev > n_host ? 0u : *n_dev) : n_host;  // overflowed arena: sort nothing
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if (tid == 0) s_tile = atomicAdd(ticket, 1u);
 	for (int i = tid; i < (RS_THREADS / 32) * RS_RADIX; i += RS_THREADS) (&s_warp_hist[0][0])[i] = 0;

@@ -1,0 +1,290 @@
+// Trainer step kernels: the per-Gaussian backward fused with the activations' backward, the Adam update of
+// all 59 parameters of the Gaussian and the densification statistics — one kernel per iteration, one read
+// and one write of every parameter / moment, no gradient tensor in memory.
+//
+// Replaces, per iteration of reference GaussianMapper::trainForOneIteration (src/gaussian_mapper.cpp:614-774):
+//   computeCov2DCUDA + preprocessCUDA backward (cuda_rasterizer/backward.cu:144-396),
+//   autograd through sigmoid / exp / normalize / cat (src/gaussian_model.cpp:48-71),
+//   9 torch::zeros gradient tensors incl. [P,16,3] (src/rasterize_points.cu:148-157),
+//   max_radii2D / addDensificationStats (gaussian_mapper.cpp:714-719, gaussian_model.cpp:817-831),
+//   torch::optim::Adam::step over 6 parameter groups + zero_grad (gaussian_mapper.cpp:769-772).
+//
+// Data movement: the [P,15,3] SH rows (180 B per Gaussian, 76 % of the parameter bytes) of parameters and both
+// moments are moved global -> shared -> global with 1-D TMA bulk copies (one 23 KB copy per tensor per
+// 128-Gaussian block, perfectly coalesced); each thread then walks its own row in shared memory
+// (row stride 45 words: bank-conflict free).
+#include "psb_backward.cuh"
+#include "psb_train.h"
+
+namespace psb {
+
+namespace {
+
+constexpr int TB = 128;        // Gaussians per block
+constexpr int REST = 45;       // floats per f_rest row (15 coefficients x 3 channels)
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes)
+{
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+struct AdamCoef { float beta1, beta2, eps, inv_bc1, bc2_sqrt; };
+
+// torch::optim::Adam single-tensor update (LibTorch adam.cpp): exp_avg.mul_(b1).add_(g, 1-b1);
+// exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2); denom = exp_avg_sq.sqrt()/sqrt(bc2) + eps; p.addcdiv_(exp_avg, denom, -lr/bc1)
+__device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, float lr, const AdamCoef& c)
+{
+	m = m * c.beta1 + (1.f - c.beta1) * g;
+	v = v * c.beta2 + (1.f - c.beta2) * g * g;
+	const float denom = sqrtf(v) / c.bc2_sqrt + c.eps;
+	p = p - (lr * c.inv_bc1) * (m / denom);
+}
+
+// ADAM = true : fused update (parameters and moments updated in place).
+// ADAM = false: gradients w.r.t. the RAW parameters are written to `grads` (6 segments, reference tensor shapes)
+//               for the data-parallel path (all-reduce between this kernel and adam_kernel).
+template <bool ADAM>
+__global__ void __launch_bounds__(TB) fused_backward_kernel(int P, TrainTensors t, Camera cam, GeomState geom, float4* __restrict__ sink,
+                                                            StepHyper h, GradSegments grads, DensifyStats st,
+                                                            const uint32_t* __restrict__ counters, uint32_t capacity)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	float* s_p = reinterpret_cast<float*>(smem_raw);  // [TB*REST] f_rest parameters
+	float* s_m = s_p + TB * REST;                     // ADAM: exp_avg rows      | !ADAM: gradient rows (output)
+	float* s_v = s_m + TB * REST;                     // ADAM: exp_avg_sq rows
+	__shared__ __align__(8) uint64_t s_bar;
+
+	// A binning arena that turned out too small leaves the tile lists incomplete: make the step a no-op
+	// (the host sees the same counter, grows the arena and repeats the step).
+	if (counters[0] > capacity) return;
+
+	const int tid = threadIdx.x;
+	const int base = blockIdx.x * TB;
+	const int rows = min(TB, P - base);
+	const uint32_t row_bytes = (uint32_t)rows * REST * sizeof(float);
+	const uint32_t bulk_bytes = row_bytes & ~15u;
+	const int rem_floats = (int)(row_bytes & 15u) / 4;
+	const size_t goff = (size_t)base * REST;
+
+	if (tid == 0) {
+		mbar_init(&s_bar, 1);
+		mbar_fence_init();
+		mbar_arrive_expect_tx(&s_bar, ADAM ? 3 * bulk_bytes : bulk_bytes);
+		bulk_g2s(s_p, t.p[2] + goff, bulk_bytes, &s_bar);
+		if (ADAM) {
+			bulk_g2s(s_m, t.m[2] + goff, bulk_bytes, &s_bar);
+			bulk_g2s(s_v, t.v[2] + goff, bulk_bytes, &s_bar);
+		}
+		for (int i = 0; i < rem_floats; i++) {  // < 16 trailing bytes of the last block
+			const int o = bulk_bytes / 4 + i;
+			s_p[o] = t.p[2][goff + o];
+			if (ADAM) { s_m[o] = t.m[2][goff + o]; s_v[o] = t.v[2][goff + o]; }
+		}
+	}
+
+	const int idx = base + tid;
+	const bool valid = idx < P;
+	AdamCoef ac;
+	ac.beta1 = h.beta1; ac.beta2 = h.beta2; ac.eps = h.eps; ac.inv_bc1 = h.inv_bc1; ac.bc2_sqrt = h.bc2_sqrt;
+
+	// ---- per-Gaussian loads that do not depend on the staged rows
+	bool visible = false;
+	float3 g_xyz = make_float3(0, 0, 0), g_dc = make_float3(0, 0, 0), g_scale = make_float3(0, 0, 0);
+	float4 g_rot = make_float4(0, 0, 0, 0);
+	float g_opac = 0.f;
+	float3 mean = make_float3(0, 0, 0), dc = make_float3(0, 0, 0);
+	float3 dL_dcolor = make_float3(0, 0, 0);
+	uint32_t clamp_bits = 0;
+	float3 sh_dmean = make_float3(0, 0, 0);
+	if (valid) {
+		visible = geom.tiles_touched[idx] != 0;
+		const float4 s0 = sink[3 * idx], s1 = sink[3 * idx + 1], s2 = sink[3 * idx + 2];
+		const float4 z = make_float4(0, 0, 0, 0);
+		sink[3 * idx] = z; sink[3 * idx + 1] = z; sink[3 * idx + 2] = z;  // ready for the next iteration
+		if (visible) {
+			// sink row: [0,1] mean2D.xy | [3,4,6] conic.xyw | [7] opacity | [8,9,10] rgb
+			const float2 dL_dmean2D = make_float2(s0.x, s0.y);
+			const float3 dL_dconic = make_float3(s0.w, s1.x, s1.z);
+			const float dL_dopacity = s1.w;
+			dL_dcolor = make_float3(s2.x, s2.y, s2.z);
+			mean = make_float3(t.p[0][3 * idx], t.p[0][3 * idx + 1], t.p[0][3 * idx + 2]);
+			dc = make_float3(t.p[1][3 * idx], t.p[1][3 * idx + 1], t.p[1][3 * idx + 2]);
+			const float3 sraw = make_float3(t.p[4][3 * idx], t.p[4][3 * idx + 1], t.p[4][3 * idx + 2]);
+			const float4 qraw = reinterpret_cast<const float4*>(t.p[5])[idx];
+			const float oraw = t.p[3][idx];
+			clamp_bits = __float_as_uint(geom.rec[idx].q2.w);
+			// activations exactly as in the forward (preprocess_fwd_kernel<RAW>)
+			const float3 s = make_float3(expf(sraw.x), expf(sraw.y), expf(sraw.z));
+			const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
+			const float4 q = make_float4(qraw.x / qn, qraw.y / qn, qraw.z / qn, qraw.w / qn);
+			const float sig = 1.0f / (1.0f + expf(-oraw));
+			float cov3D[6], dL_dcov[6];
+			cov3d_from_scale_rot(s, 1.0f, q, cov3D);
+			gaussian_backward_geom(cam, mean, cov3D, dL_dmean2D, dL_dconic, g_xyz, dL_dcov);
+			float3 dL_dscale;
+			float4 dL_drot;
+			cov3d_backward(s, 1.0f, q, dL_dcov, dL_dscale, dL_drot);
+			// autograd of the activations (src/gaussian_model.cpp:48-71): exp, normalize, sigmoid
+			g_scale = make_float3(dL_dscale.x * s.x, dL_dscale.y * s.y, dL_dscale.z * s.z);
+			const float qd = q.x * dL_drot.x + q.y * dL_drot.y + q.z * dL_drot.z + q.w * dL_drot.w;
+			g_rot = make_float4((dL_drot.x - q.x * qd) / qn, (dL_drot.y - q.y * qd) / qn, (dL_drot.z - q.z * qd) / qn, (dL_drot.w - q.w * qd) / qn);
+			g_opac = dL_dopacity * sig * (1.0f - sig);
+			if (st.enabled) {
+				st.max_radii2D[idx] = fmaxf(st.max_radii2D[idx], (float)__float_as_int(geom.rec[idx].q2.z));
+				st.xyz_gradient_accum[idx] += sqrtf(dL_dmean2D.x * dL_dmean2D.x + dL_dmean2D.y * dL_dmean2D.y);
+				st.denom[idx] += 1.0f;
+			}
+		}
+	}
+
+	mbar_wait(&s_bar, 0);  // f_rest rows have landed
+	__syncthreads();       // (also publishes thread 0's trailing plain stores)
+
+	float* rp = s_p + tid * REST;
+	float* rm = s_m + tid * REST;
+	float* rv = s_v + tid * REST;
+	const int nact = ((h.D + 1) * (h.D + 1) - 1) * 3;  // f_rest elements that receive a gradient
+	if (valid) {
+		if (visible) {
+			const float3 campos = make_float3(cam.campos[0], cam.campos[1], cam.campos[2]);
+			sh_dmean = sh_backward_t(
+				h.D, mean, campos, clamp_bits, dL_dcolor,
+				[&](int k, int ch) { return k == 0 ? (ch == 0 ? dc.x : (ch == 1 ? dc.y : dc.z)) : rp[3 * (k - 1) + ch]; },
+				[&](int k, int ch, float g) {
+					if (k == 0) { if (ch == 0) g_dc.x = g; else if (ch == 1) g_dc.y = g; else g_dc.z = g; }
+					else {
+						const int e = 3 * (k - 1) + ch;
+						if (ADAM) adam1(rp[e], rm[e], rv[e], g, h.lr[2], ac);
+						else rm[e] = g;
+					}
+				});
+			g_xyz.x += sh_dmean.x; g_xyz.y += sh_dmean.y; g_xyz.z += sh_dmean.z;
+		}
+		for (int e = visible ? nact : 0; e < REST; e++) {
+			if (ADAM) adam1(rp[e], rm[e], rv[e], 0.f, h.lr[2], ac);
+			else rm[e] = 0.f;
+		}
+		// ---- the 14 remaining parameters
+		if (ADAM) {
+			float gx[3] = {g_xyz.x, g_xyz.y, g_xyz.z}, gd[3] = {g_dc.x, g_dc.y, g_dc.z}, gs[3] = {g_scale.x, g_scale.y, g_scale.z};
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				float p = t.p[0][3 * idx + c], m = t.m[0][3 * idx + c], v = t.v[0][3 * idx + c];
+				adam1(p, m, v, gx[c], h.lr[0], ac);
+				t.p[0][3 * idx + c] = p; t.m[0][3 * idx + c] = m; t.v[0][3 * idx + c] = v;
+				p = t.p[1][3 * idx + c]; m = t.m[1][3 * idx + c]; v = t.v[1][3 * idx + c];
+				adam1(p, m, v, gd[c], h.lr[1], ac);
+				t.p[1][3 * idx + c] = p; t.m[1][3 * idx + c] = m; t.v[1][3 * idx + c] = v;
+				p = t.p[4][3 * idx + c]; m = t.m[4][3 * idx + c]; v = t.v[4][3 * idx + c];
+				adam1(p, m, v, gs[c], h.lr[4], ac);
+				t.p[4][3 * idx + c] = p; t.m[4][3 * idx + c] = m; t.v[4][3 * idx + c] = v;
+			}
+			{
+				float p = t.p[3][idx], m = t.m[3][idx], v = t.v[3][idx];
+				adam1(p, m, v, g_opac, h.lr[3], ac);
+				t.p[3][idx] = p; t.m[3][idx] = m; t.v[3][idx] = v;
+			}
+			{
+				float4 p = reinterpret_cast<float4*>(t.p[5])[idx], m = reinterpret_cast<float4*>(t.m[5])[idx], v = reinterpret_cast<float4*>(t.v[5])[idx];
+				adam1(p.x, m.x, v.x, g_rot.x, h.lr[5], ac);
+				adam1(p.y, m.y, v.y, g_rot.y, h.lr[5], ac);
+				adam1(p.z, m.z, v.z, g_rot.z, h.lr[5], ac);
+				adam1(p.w, m.w, v.w, g_rot.w, h.lr[5], ac);
+				reinterpret_cast<float4*>(t.p[5])[idx] = p; reinterpret_cast<float4*>(t.m[5])[idx] = m; reinterpret_cast<float4*>(t.v[5])[idx] = v;
+			}
+		} else {
+			grads.g[0][3 * idx] = g_xyz.x; grads.g[0][3 * idx + 1] = g_xyz.y; grads.g[0][3 * idx + 2] = g_xyz.z;
+			grads.g[1][3 * idx] = g_dc.x; grads.g[1][3 * idx + 1] = g_dc.y; grads.g[1][3 * idx + 2] = g_dc.z;
+			grads.g[3][idx] = g_opac;
+			grads.g[4][3 * idx] = g_scale.x; grads.g[4][3 * idx + 1] = g_scale.y; grads.g[4][3 * idx + 2] = g_scale.z;
+			reinterpret_cast<float4*>(grads.g[5])[idx] = g_rot;
+		}
+	}
+
+	// ---- rows back to global memory through the async proxy
+	fence_proxy_async_smem();
+	__syncthreads();
+	if (tid == 0) {
+		if (ADAM) {
+			bulk_s2g(t.p[2] + goff, s_p, bulk_bytes);
+			bulk_s2g(t.m[2] + goff, s_m, bulk_bytes);
+			bulk_s2g(t.v[2] + goff, s_v, bulk_bytes);
+		} else {
+			bulk_s2g(grads.g[2] + goff, s_m, bulk_bytes);
+		}
+		bulk_commit();
+		for (int i = 0; i < rem_floats; i++) {
+			const int o = bulk_bytes / 4 + i;
+			if (ADAM) { t.p[2][goff + o] = s_p[o]; t.m[2][goff + o] = s_m[o]; t.v[2][goff + o] = s_v[o]; }
+			else grads.g[2][goff + o] = s_m[o];
+		}
+		bulk_wait_read0();  // shared memory must stay alive until the TMA engine has read it
+	}
+}
+
+// Plain Adam over one flat tensor (data-parallel path, after the gradient all-reduce). 128-bit accesses.
+__global__ void __launch_bounds__(256) adam_kernel(size_t n4, float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v,
+                                                   const float4* __restrict__ g, float lr, AdamCoef c, float grad_scale)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n4) return;
+	float4 pp = p[i], mm = m[i], vv = v[i];
+	const float4 gg = g[i];
+	adam1(pp.x, mm.x, vv.x, gg.x * grad_scale, lr, c);
+	adam1(pp.y, mm.y, vv.y, gg.y * grad_scale, lr, c);
+	adam1(pp.z, mm.z, vv.z, gg.z * grad_scale, lr, c);
+	adam1(pp.w, mm.w, vv.w, gg.w * grad_scale, lr, c);
+	p[i] = pp; m[i] = mm; v[i] = vv;
+}
+__global__ void adam_tail_kernel(size_t start, size_t n, float* p, float* m, float* v, const float* g, float lr, AdamCoef c, float grad_scale)
+{
+	const size_t i = start + threadIdx.x;
+	if (i < n) adam1(p[i], m[i], v[i], g[i] * grad_scale, lr, c);
+}
+
+}  // namespace
+
+size_t fused_backward_smem_bytes(bool adam) { return (size_t)(adam ? 3 : 2) * TB * REST * sizeof(float); }
+
+int launch_fused_backward(bool adam, int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, const StepHyper& h,
+                          const GradSegments& grads, const DensifyStats& st, const uint32_t* counters, uint32_t capacity, cudaStream_t stream)
+{
+	if (P == 0) return 0;
+	static bool attr_set = false;
+	if (!attr_set) {
+		PSB_CUDA_OK(cudaFuncSetAttribute(fused_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_backward_smem_bytes(true)));
+		PSB_CUDA_OK(cudaFuncSetAttribute(fused_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_backward_smem_bytes(false)));
+		attr_set = true;
+	}
+	const int grid = cdiv(P, TB);
+	if (adam)
+		fused_backward_kernel<true><<<grid, TB, fused_backward_smem_bytes(true), stream>>>(P, t, cam, geom, reinterpret_cast<float4*>(sink), h, grads, st, counters, capacity);
+	else
+		fused_backward_kernel<false><<<grid, TB, fused_backward_smem_bytes(false), stream>>>(P, t, cam, geom, reinterpret_cast<float4*>(sink), h, grads, st, counters, capacity);
+	PSB_LAUNCH_OK();
+	return 0;
+}
+
+int launch_adam(size_t n, float* p, float* m, float* v, const float* g, float lr, const StepHyper& h, float grad_scale, cudaStream_t stream)
+{
+	if (n == 0) return 0;
+	AdamCoef c;
+	c.beta1 = h.beta1; c.beta2 = h.beta2; c.eps = h.eps; c.inv_bc1 = h.inv_bc1; c.bc2_sqrt = h.bc2_sqrt;
+	const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(g)) & 15) == 0;
+	const size_t n4 = aligned ? n / 4 : 0;
+	if (n4) {
+		adam_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(n4, reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
+		                                                             reinterpret_cast<const float4*>(g), lr, c, grad_scale);
+		PSB_LAUNCH_OK();
+	}
+	for (size_t s = n4 * 4; s < n; s += 256) {
+		adam_tail_kernel<<<1, 256, 0, stream>>>(s, n, p, m, v, g, lr, c, grad_scale);
+		PSB_LAUNCH_OK();
+	}
+	return 0;
+}
+
+}  // namespace psb

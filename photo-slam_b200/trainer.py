@@ -1,0 +1,314 @@
+"""Host-side mirror of the reference's trainer-level surface for the hot path, on the psb200 C-ABI.
+
+  GaussianOptimizationParams   reference include/gaussian_parameters.h:49-96 (values: cfg/gaussian_mapper/RGB-D/Replica/replica_rgbd.yaml:53-74)
+  GaussianModel                reference include/gaussian_model.h:59-193 — the tensors, Adam state, learning-rate
+                               handling (trainingSetup / updateLearningRate / set*LearningRate / exponLrFunc,
+                               src/gaussian_model.cpp:477-554, 1118-1131)
+  GaussianTrainer              reference GaussianMapper::trainForOneIteration (src/gaussian_mapper.cpp:614-774) /
+                               GaussianTrainer::trainingOnce (src/gaussian_trainer.cpp:31-135): one iteration =
+                               render, L1 + DSSIM, backward, densification statistics, Adam step — here ONE call
+                               into psb_trainer_step.
+PyTorch provides device memory, streams and (for the data-parallel variant) torch.distributed.
+"""
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+GROUPS = ("xyz", "features_dc", "features_rest", "opacity", "scaling", "rotation")
+
+
+class _Model(C.Structure):
+    _fields_ = [("param", C.c_void_p * 6), ("exp_avg", C.c_void_p * 6), ("exp_avg_sq", C.c_void_p * 6),
+                ("max_radii2D", C.c_void_p), ("xyz_gradient_accum", C.c_void_p), ("denom", C.c_void_p)]
+
+
+class _Camera(C.Structure):
+    _fields_ = [("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p), ("tan_fovx", C.c_float),
+                ("tan_fovy", C.c_float), ("width", C.c_int), ("height", C.c_int)]
+
+
+class _Step(C.Structure):
+    _fields_ = [("lr", C.c_float * 6), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("step", C.c_int),
+                ("lambda_dssim", C.c_float), ("sh_degree", C.c_int), ("update_densify_stats", C.c_int)]
+
+
+def _bind():
+    L = _lib.lib()
+    if getattr(L, "_trainer_bound", False):
+        return L
+    vp = C.c_void_p
+    L.psb_trainer_create.argtypes = [C.POINTER(vp)]
+    L.psb_trainer_destroy.argtypes = [vp]
+    L.psb_trainer_render.argtypes = [vp, C.c_int, C.c_int, C.POINTER(_Model), C.POINTER(_Camera), vp, C.c_int, vp, vp, vp]
+    L.psb_trainer_step.argtypes = [vp, C.c_int, C.c_int, C.POINTER(_Model), C.POINTER(_Camera), vp, vp, vp, C.POINTER(_Step), vp, vp, vp]
+    L.psb_trainer_backward.argtypes = [vp, C.c_int, C.c_int, C.POINTER(_Model), C.POINTER(_Camera), vp, vp, vp, C.POINTER(_Step), vp, vp,
+                                       C.POINTER(vp), vp]
+    L.psb_adam_update.argtypes = [C.c_int, C.c_int, C.POINTER(_Model), C.POINTER(vp), C.POINTER(_Step), C.c_float, vp]
+    L.psb_trainer_result.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int), vp]
+    L.psb_loss.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_float, vp, C.POINTER(C.c_float), vp]
+    for n in ("psb_trainer_create", "psb_trainer_destroy", "psb_trainer_render", "psb_trainer_step", "psb_trainer_backward",
+              "psb_adam_update", "psb_trainer_result", "psb_loss"):
+        getattr(L, n).restype = C.c_int
+    L._trainer_bound = True
+    return L
+
+
+@dataclass
+class GaussianOptimizationParams:
+    iterations: int = 30100
+    position_lr_init: float = 0.00032
+    position_lr_final: float = 0.00032
+    position_lr_delay_mult: float = 0.01
+    position_lr_max_steps: int = 24
+    feature_lr: float = 0.0025
+    opacity_lr: float = 0.05
+    scaling_lr: float = 0.005
+    rotation_lr: float = 0.001
+    percent_dense: float = 0.01
+    lambda_dssim: float = 0.2
+    densification_interval: int = 100
+    opacity_reset_interval: int = 0
+    densify_from_iter: int = 600
+    densify_until_iter: int = 15000
+    densify_grad_threshold: float = 0.001
+
+
+class GaussianModel:
+    """Parameter tensors in the reference's layout + Adam state + learning rates."""
+
+    def __init__(self, sh_degree=3, device="cuda"):
+        self.max_sh_degree_ = sh_degree
+        self.active_sh_degree_ = 0
+        self.device = torch.device(device)
+        self.spatial_lr_scale_ = 1.0
+        self.lr_ = [0.0] * 6
+        self.step_ = 0
+        self.lr_delay_steps_ = 0
+
+    @classmethod
+    def from_numpy(cls, scene, device="cuda", sh_degree=3):
+        m = cls(sh_degree, device)
+        t = lambda a: torch.from_numpy(a).to(m.device).contiguous()
+        m.xyz_, m.features_dc_, m.features_rest_ = t(scene["xyz"]), t(scene["features_dc"]), t(scene["features_rest"])
+        m.opacity_, m.scaling_, m.rotation_ = t(scene["opacity"]), t(scene["scaling"]), t(scene["rotation"])
+        m.active_sh_degree_ = sh_degree
+        return m
+
+    def tensors(self):
+        return [self.xyz_, self.features_dc_, self.features_rest_, self.opacity_, self.scaling_, self.rotation_]
+
+    def num_points(self):
+        return self.xyz_.size(0)
+
+    # --- reference GaussianModel::trainingSetup (gaussian_model.cpp:477-509)
+    def trainingSetup(self, args: GaussianOptimizationParams):
+        P = self.num_points()
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=self.device)
+        self.xyz_gradient_accum_, self.denom_, self.max_radii2D_ = z(P, 1), z(P, 1), z(P)
+        self.exp_avg_ = [torch.zeros_like(t) for t in self.tensors()]
+        self.exp_avg_sq_ = [torch.zeros_like(t) for t in self.tensors()]
+        self.step_ = 0
+        self.lr_ = [args.position_lr_init * self.spatial_lr_scale_, args.feature_lr, args.feature_lr / 20.0, args.opacity_lr,
+                    args.scaling_lr, args.rotation_lr]
+        self.lr_init_ = args.position_lr_init * self.spatial_lr_scale_
+        self.lr_final_ = args.position_lr_final * self.spatial_lr_scale_
+        self.lr_delay_mult_ = args.position_lr_delay_mult
+        self.max_steps_ = args.position_lr_max_steps
+
+    def exponLrFunc(self, step):
+        if step < 0 or (self.lr_init_ == 0.0 and self.lr_final_ == 0.0):
+            return 0.0
+        if self.lr_delay_steps_ > 0:
+            delay = self.lr_delay_mult_ + (1.0 - self.lr_delay_mult_) * math.sin(0.5 * math.pi * min(max(step / self.lr_delay_steps_, 0.0), 1.0))
+        else:
+            delay = 1.0
+        t = min(max(step / self.max_steps_, 0.0), 1.0)
+        return delay * math.exp(math.log(self.lr_init_) * (1 - t) + math.log(self.lr_final_) * t)
+
+    def updateLearningRate(self, step):
+        self.lr_[0] = self.exponLrFunc(step)
+        return self.lr_[0]
+
+    def setPositionLearningRate(self, lr): self.lr_[0] = lr * self.spatial_lr_scale_
+    def setFeatureLearningRate(self, lr): self.lr_[1], self.lr_[2] = lr, lr / 20.0
+    def setOpacityLearningRate(self, lr): self.lr_[3] = lr
+    def setScalingLearningRate(self, lr): self.lr_[4] = lr
+    def setRotationLearningRate(self, lr): self.lr_[5] = lr
+    def setShDegree(self, d): self.active_sh_degree_ = min(max(d, 0), self.max_sh_degree_)
+
+    def oneUpShDegree(self):
+        if self.active_sh_degree_ < self.max_sh_degree_:
+            self.active_sh_degree_ += 1
+
+    def _cmodel(self, with_state=True):
+        m = _Model()
+        for i, t in enumerate(self.tensors()):
+            assert t.is_contiguous() and t.dtype == torch.float32
+            m.param[i] = t.data_ptr()
+            if with_state:
+                m.exp_avg[i] = self.exp_avg_[i].data_ptr()
+                m.exp_avg_sq[i] = self.exp_avg_sq_[i].data_ptr()
+        if with_state:
+            m.max_radii2D = self.max_radii2D_.data_ptr()
+            m.xyz_gradient_accum = self.xyz_gradient_accum_.data_ptr()
+            m.denom = self.denom_.data_ptr()
+        return m
+
+
+def _ccamera(cam):
+    c = _Camera()
+    c.viewmatrix, c.projmatrix, c.campos = cam["viewmatrix"].data_ptr(), cam["projmatrix"].data_ptr(), cam["campos"].data_ptr()
+    c.tan_fovx, c.tan_fovy, c.width, c.height = float(cam["tanfovx"]), float(cam["tanfovy"]), int(cam["W"]), int(cam["H"])
+    return c
+
+
+class GaussianTrainer:
+    """One fused training iteration per call. `cam` = dict(viewmatrix, projmatrix, campos: device tensors; tanfovx, tanfovy, W, H)."""
+
+    def __init__(self, model: GaussianModel, opt: GaussianOptimizationParams = None, background=None):
+        self.L = _bind()
+        self.model = model
+        self.opt = opt or GaussianOptimizationParams()
+        h = C.c_void_p()
+        _lib.check(self.L.psb_trainer_create(C.byref(h)), "psb_trainer_create")
+        self.h = h
+        self.background = background if background is not None else torch.zeros(3, device=model.device)
+        self.iteration = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.psb_trainer_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _cstep(self, densify_stats=True):
+        m = self.model
+        s = _Step()
+        for i in range(6):
+            s.lr[i] = m.lr_[i]
+        s.beta1, s.beta2, s.eps = 0.9, 0.999, 1e-15
+        s.step = m.step_ + 1
+        s.lambda_dssim = self.opt.lambda_dssim
+        s.sh_degree = m.active_sh_degree_
+        s.update_densify_stats = int(densify_stats)
+        return s
+
+    def render(self, cam, out=None, radii=None):
+        m = self.model
+        out = out if out is not None else torch.empty((3, cam["H"], cam["W"]), device=m.device)
+        cm, cc = m._cmodel(False), _ccamera(cam)
+        _lib.check(self.L.psb_trainer_render(self.h, m.num_points(), 16, C.byref(cm), C.byref(cc), self.background.data_ptr(),
+                                             m.active_sh_degree_, out.data_ptr(), radii.data_ptr() if radii is not None else None,
+                                             torch.cuda.current_stream().cuda_stream), "psb_trainer_render")
+        self._last_render = (cam, out, radii)
+        self._last = None
+        return out
+
+    def trainForOneIteration(self, cam, gt_image, mask=None, out_color=None, radii=None, densify_stats=None):
+        """Enqueues render -> loss -> backward -> Adam on the current stream (no host sync)."""
+        m = self.model
+        self.iteration += 1
+        if densify_stats is None:
+            densify_stats = self.iteration < self.opt.densify_until_iter
+        cm, cc, cs = m._cmodel(), _ccamera(cam), self._cstep(densify_stats)
+        _lib.check(self.L.psb_trainer_step(self.h, m.num_points(), 16, C.byref(cm), C.byref(cc), self.background.data_ptr(),
+                                           gt_image.data_ptr(), mask.data_ptr() if mask is not None else None, C.byref(cs),
+                                           out_color.data_ptr() if out_color is not None else None,
+                                           radii.data_ptr() if radii is not None else None,
+                                           torch.cuda.current_stream().cuda_stream), "psb_trainer_step")
+        m.step_ += 1
+        self._last = (cam, gt_image, mask, out_color, radii, densify_stats)
+
+    def result(self):
+        """Blocks; -> (loss, l1, ssim, num_rendered). Transparently repeats the step if the arena had to grow."""
+        out, n = (C.c_float * 3)(), C.c_int()
+        rc = self.L.psb_trainer_result(self.h, out, C.byref(n), torch.cuda.current_stream().cuda_stream)
+        if rc == -4 and getattr(self, "_last", None) is None:  # a render overflowed the arena: render again
+            cam, o, rad = self._last_render
+            self.render(cam, o, rad)
+            return self.result()
+        if rc == -4:  # PSB_ERR_RETRY: the step was a no-op
+            self.model.step_ -= 1
+            self.iteration -= 1
+            cam, gt, mask, oc, rad, ds = self._last
+            self.trainForOneIteration(cam, gt, mask, oc, rad, ds)
+            return self.result()
+        _lib.check(rc, "psb_trainer_result")
+        return out[0], out[1], out[2], n.value
+
+    STAGES = ("preprocess", "depth_sort_scan", "binning", "render_fwd", "loss", "render_bwd", "backward_adam")
+
+    def set_profiling(self, enable=True):
+        self.L.psb_trainer_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        _lib.check(self.L.psb_trainer_set_profiling(self.h, int(enable)), "psb_trainer_set_profiling")
+
+    def stage_times(self):
+        """ms per stage of the last profiled step (CUDA events on the step's stream)."""
+        ms = (C.c_float * 7)()
+        self.L.psb_trainer_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
+        _lib.check(self.L.psb_trainer_stage_times(self.h, ms, 7), "psb_trainer_stage_times")
+        return dict(zip(self.STAGES, [float(x) for x in ms]))
+
+    def trainingOnce(self, cam, gt_image, mask=None):
+        """Reference-style blocking iteration: returns the loss like loss.item() (gaussian_mapper.cpp:705)."""
+        self.trainForOneIteration(cam, gt_image, mask)
+        return self.result()[0]
+
+
+class DataParallelTrainer(GaussianTrainer):
+    """Keyframe-sharded data parallelism: replicated Gaussians, rank r renders its own view,
+    ONE all-reduce (sum) over the flat [P*59] raw-parameter gradient buffer, then the same Adam update on
+    every rank with grad_scale = 1/world (mean over views keeps the learning-rate scale of one view per step)."""
+
+    def __init__(self, model, opt=None, background=None, group=None):
+        super().__init__(model, opt, background)
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        P = model.num_points()
+        self.sizes = [3, 3, 45, 1, 3, 4]
+        self.flat = torch.zeros(P * 59, dtype=torch.float32, device=model.device)
+        offs, o = [], 0
+        for s in self.sizes:
+            offs.append(o)
+            o += P * s
+        self.segs = [self.flat[offs[i]: offs[i] + P * self.sizes[i]] for i in range(6)]
+
+    def trainForOneIteration(self, cam, gt_image, mask=None, out_color=None, radii=None, densify_stats=None):
+        m = self.model
+        self.iteration += 1
+        if densify_stats is None:
+            densify_stats = self.iteration < self.opt.densify_until_iter
+        cm, cc, cs = m._cmodel(), _ccamera(cam), self._cstep(densify_stats)
+        ptrs = (C.c_void_p * 6)(*[s.data_ptr() for s in self.segs])
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(self.L.psb_trainer_backward(self.h, m.num_points(), 16, C.byref(cm), C.byref(cc), self.background.data_ptr(),
+                                               gt_image.data_ptr(), mask.data_ptr() if mask is not None else None, C.byref(cs),
+                                               out_color.data_ptr() if out_color is not None else None,
+                                               radii.data_ptr() if radii is not None else None, ptrs, stream), "psb_trainer_backward")
+        if self.world > 1:
+            self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM, group=self.group)
+            if densify_stats:
+                # statistics of the K views of this step: sums for the accumulators, max for the radii
+                self.dist.all_reduce(m.max_radii2D_, op=self.dist.ReduceOp.MAX, group=self.group)
+        _lib.check(self.L.psb_adam_update(m.num_points(), 16, C.byref(cm), ptrs, C.byref(cs), 1.0 / self.world, stream), "psb_adam_update")
+        m.step_ += 1
+        self._last = (cam, gt_image, mask, out_color, radii, densify_stats)
+
+
+def fused_loss(image, gt, mask=None, lambda_dssim=0.2, want_grad=True):
+    """-> (loss, l1, ssim, dL_dimage or None) through psb_loss."""
+    L = _bind()
+    _, H, W = image.shape
+    grad = torch.empty_like(image) if want_grad else None
+    out = (C.c_float * 3)()
+    _lib.check(L.psb_loss(H, W, image.contiguous().data_ptr(), gt.contiguous().data_ptr(), mask.data_ptr() if mask is not None else None,
+                          float(lambda_dssim), grad.data_ptr() if want_grad else None, out, torch.cuda.current_stream().cuda_stream), "psb_loss")
+    return out[0], out[1], out[2], grad
