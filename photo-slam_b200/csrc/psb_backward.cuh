@@ -25,7 +25,7 @@ __device__ __forceinline__ float3 dnormvdv(float3 v, float3 dv)
 // first put, so `put` may update the coefficient in place. Returns the view-direction contribution to dL/dmean.
 template <typename Get, typename Put>
 __device__ __forceinline__ float3 sh_backward_t(int deg, const float3 pos, const float3 campos, uint32_t clamp_bits,
-                                                const float3 dL_dcolor, Get get, Put put)
+                                                const float3 dL_dcolor, Get get, Put put, float* w_out = nullptr)
 {
 	const float3 dir_orig = make_float3(pos.x - campos.x, pos.y - campos.y, pos.z - campos.z);
 	const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
@@ -67,6 +67,10 @@ __device__ __forceinline__ float3 sh_backward_t(int deg, const float3 pos, const
 	w[9] = kSH_C3_0 * y * (3.f * xx - yy); w[10] = kSH_C3_1 * xy * z; w[11] = kSH_C3_2 * y * (4.f * zz - xx - yy);
 	w[12] = kSH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy); w[13] = kSH_C3_4 * x * (4.f * zz - xx - yy); w[14] = kSH_C3_5 * z * (xx - yy);
 	w[15] = kSH_C3_6 * x * (xx - 3.f * yy);
+	if (w_out) {
+#pragma unroll
+		for (int k = 0; k < 16; k++) w_out[k] = w[k];
+	}
 	const int ncoef = (deg + 1) * (deg + 1);
 #pragma unroll
 	for (int k = 0; k < 16; k++) {

@@ -31,30 +31,39 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-struct AdamCoef { float beta1, beta2, eps, inv_bc1, bc2_sqrt; };
+struct AdamCoef { float beta1, beta2, eps, inv_bc1, inv_bc2_sqrt; };
 
 // torch::optim::Adam single-tensor update (LibTorch adam.cpp): exp_avg.mul_(b1).add_(g, 1-b1);
-// exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2); denom = exp_avg_sq.sqrt()/sqrt(bc2) + eps; p.addcdiv_(exp_avg, denom, -lr/bc1)
-__device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, float lr, const AdamCoef& c)
+// exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2); denom = exp_avg_sq.sqrt()/sqrt(bc2) + eps; p.addcdiv_(exp_avg, denom, -lr/bc1).
+// sqrt and the division go through the MUFU unit (rsqrt / rcp, ~1-2 ulp): 59 IEEE sqrt+div sequences per
+// Gaussian would otherwise make this HBM-streaming kernel issue-bound.
+__device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, float lr_eff, const AdamCoef& c)
 {
 	m = m * c.beta1 + (1.f - c.beta1) * g;
 	v = v * c.beta2 + (1.f - c.beta2) * g * g;
-	const float denom = sqrtf(v) / c.bc2_sqrt + c.eps;
-	p = p - (lr * c.inv_bc1) * (m / denom);
+	const float sq = v > 0.f ? v * rsqrtf(v) : 0.f;
+	const float denom = sq * c.inv_bc2_sqrt + c.eps;
+	p = p - lr_eff * __fdividef(m, denom);
 }
 
 // ADAM = true : fused update (parameters and moments updated in place).
 // ADAM = false: gradients w.r.t. the RAW parameters are written to `grads` (6 segments, reference tensor shapes)
 //               for the data-parallel path (all-reduce between this kernel and adam_kernel).
+//
+// Block = 128 Gaussians. Phase 1 (one thread per Gaussian): screen-space sums -> gradients of the 14 small
+// parameters (+ their Adam update), densification statistics, and the per-Gaussian SH "seed": the 16 basis
+// weights w_k(dir) and the clamp-masked dL/dRGB, from which every SH gradient is w_k * dL/dRGB[ch].
+// The f_rest parameter rows the SH backward has to READ per Gaussian (view-direction term) arrive by one TMA
+// bulk copy per block. Phase 2 (whole block, element-wise, 128-bit coalesced): Adam over the block's
+// [128 x 45] f_rest chunk, gradient looked up from the seeds in shared memory.
 template <bool ADAM>
 __global__ void __launch_bounds__(TB) fused_backward_kernel(int P, TrainTensors t, Camera cam, GeomState geom, float4* __restrict__ sink,
                                                             StepHyper h, GradSegments grads, DensifyStats st,
                                                             const uint32_t* __restrict__ counters, uint32_t capacity)
 {
-	extern __shared__ __align__(128) unsigned char smem_raw[];
-	float* s_p = reinterpret_cast<float*>(smem_raw);  // [TB*REST] f_rest parameters
-	float* s_m = s_p + TB * REST;                     // ADAM: exp_avg rows      | !ADAM: gradient rows (output)
-	float* s_v = s_m + TB * REST;                     // ADAM: exp_avg_sq rows
+	__shared__ __align__(128) float s_p[TB * REST];  // f_rest parameter rows of this block (TMA destination)
+	__shared__ float s_w[TB][17];                    // SH basis weights per Gaussian (k = 0..15), padded
+	__shared__ float s_g[TB][4];                     // clamp-masked dL/dRGB per Gaussian (0 when not visible)
 	__shared__ __align__(8) uint64_t s_bar;
 
 	// A binning arena that turned out too small leaves the tile lists incomplete: make the step a no-op
@@ -72,33 +81,24 @@ __global__ void __launch_bounds__(TB) fused_backward_kernel(int P, TrainTensors 
 	if (tid == 0) {
 		mbar_init(&s_bar, 1);
 		mbar_fence_init();
-		mbar_arrive_expect_tx(&s_bar, ADAM ? 3 * bulk_bytes : bulk_bytes);
+		mbar_arrive_expect_tx(&s_bar, bulk_bytes);
 		bulk_g2s(s_p, t.p[2] + goff, bulk_bytes, &s_bar);
-		if (ADAM) {
-			bulk_g2s(s_m, t.m[2] + goff, bulk_bytes, &s_bar);
-			bulk_g2s(s_v, t.v[2] + goff, bulk_bytes, &s_bar);
-		}
-		for (int i = 0; i < rem_floats; i++) {  // < 16 trailing bytes of the last block
-			const int o = bulk_bytes / 4 + i;
-			s_p[o] = t.p[2][goff + o];
-			if (ADAM) { s_m[o] = t.m[2][goff + o]; s_v[o] = t.v[2][goff + o]; }
-		}
+		for (int i = 0; i < rem_floats; i++) s_p[bulk_bytes / 4 + i] = t.p[2][goff + bulk_bytes / 4 + i];  // < 16 trailing bytes (last block)
 	}
 
 	const int idx = base + tid;
 	const bool valid = idx < P;
 	AdamCoef ac;
-	ac.beta1 = h.beta1; ac.beta2 = h.beta2; ac.eps = h.eps; ac.inv_bc1 = h.inv_bc1; ac.bc2_sqrt = h.bc2_sqrt;
+	ac.beta1 = h.beta1; ac.beta2 = h.beta2; ac.eps = h.eps; ac.inv_bc1 = h.inv_bc1; ac.inv_bc2_sqrt = 1.0f / h.bc2_sqrt;
 
-	// ---- per-Gaussian loads that do not depend on the staged rows
+	// ---- phase 1a: everything that does not need the staged rows
 	bool visible = false;
-	float3 g_xyz = make_float3(0, 0, 0), g_dc = make_float3(0, 0, 0), g_scale = make_float3(0, 0, 0);
+	float3 g_xyz = make_float3(0, 0, 0), g_scale = make_float3(0, 0, 0);
 	float4 g_rot = make_float4(0, 0, 0, 0);
 	float g_opac = 0.f;
-	float3 mean = make_float3(0, 0, 0), dc = make_float3(0, 0, 0);
+	float3 mean = make_float3(0, 0, 1), dc = make_float3(0, 0, 0);
 	float3 dL_dcolor = make_float3(0, 0, 0);
 	uint32_t clamp_bits = 0;
-	float3 sh_dmean = make_float3(0, 0, 0);
 	if (valid) {
 		visible = geom.tiles_touched[idx] != 0;
 		const float4 s0 = sink[3 * idx], s1 = sink[3 * idx + 1], s2 = sink[3 * idx + 2];
@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(TB) fused_backward_kernel(int P, TrainTensors 
 			const float3 sraw = make_float3(t.p[4][3 * idx], t.p[4][3 * idx + 1], t.p[4][3 * idx + 2]);
 			const float4 qraw = reinterpret_cast<const float4*>(t.p[5])[idx];
 			const float oraw = t.p[3][idx];
-			clamp_bits = __float_as_uint(geom.rec[idx].q2.w);
+			const float4 rq2 = geom.rec[idx].q2;
+			clamp_bits = __float_as_uint(rq2.w);
 			// activations exactly as in the forward (preprocess_fwd_kernel<RAW>)
 			const float3 s = make_float3(expf(sraw.x), expf(sraw.y), expf(sraw.z));
 			const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(TB) fused_backward_kernel(int P, TrainTensors 
 			g_rot = make_float4((dL_drot.x - q.x * qd) / qn, (dL_drot.y - q.y * qd) / qn, (dL_drot.z - q.z * qd) / qn, (dL_drot.w - q.w * qd) / qn);
 			g_opac = dL_dopacity * sig * (1.0f - sig);
 			if (st.enabled) {
-				st.max_radii2D[idx] = fmaxf(st.max_radii2D[idx], (float)__float_as_int(geom.rec[idx].q2.z));
+				st.max_radii2D[idx] = fmaxf(st.max_radii2D[idx], (float)__float_as_int(rq2.z));
 				st.xyz_gradient_accum[idx] += sqrtf(dL_dmean2D.x * dL_dmean2D.x + dL_dmean2D.y * dL_dmean2D.y);
 				st.denom[idx] += 1.0f;
 			}
@@ -143,56 +144,60 @@ __global__ void __launch_bounds__(TB) fused_backward_kernel(int P, TrainTensors 
 	mbar_wait(&s_bar, 0);  // f_rest rows have landed
 	__syncthreads();       // (also publishes thread 0's trailing plain stores)
 
-	float* rp = s_p + tid * REST;
-	float* rm = s_m + tid * REST;
-	float* rv = s_v + tid * REST;
-	const int nact = ((h.D + 1) * (h.D + 1) - 1) * 3;  // f_rest elements that receive a gradient
-	if (valid) {
+	// ---- phase 1b: SH backward seeds; the view-direction term completes dL/dxyz
+	float3 g_dc = make_float3(0, 0, 0);
+	{
+		const float* rp = s_p + tid * REST;
+		float w[16];
+#pragma unroll
+		for (int k = 0; k < 16; k++) w[k] = 0.f;
+		float gm[3] = {0.f, 0.f, 0.f};
 		if (visible) {
 			const float3 campos = make_float3(cam.campos[0], cam.campos[1], cam.campos[2]);
-			sh_dmean = sh_backward_t(
+			const float3 sh_dmean = sh_backward_t(
 				h.D, mean, campos, clamp_bits, dL_dcolor,
 				[&](int k, int ch) { return k == 0 ? (ch == 0 ? dc.x : (ch == 1 ? dc.y : dc.z)) : rp[3 * (k - 1) + ch]; },
-				[&](int k, int ch, float g) {
-					if (k == 0) { if (ch == 0) g_dc.x = g; else if (ch == 1) g_dc.y = g; else g_dc.z = g; }
-					else {
-						const int e = 3 * (k - 1) + ch;
-						if (ADAM) adam1(rp[e], rm[e], rv[e], g, h.lr[2], ac);
-						else rm[e] = g;
-					}
-				});
+				[&](int k, int ch, float g) { if (k == 0) { if (ch == 0) g_dc.x = g; else if (ch == 1) g_dc.y = g; else g_dc.z = g; } },
+				w);
 			g_xyz.x += sh_dmean.x; g_xyz.y += sh_dmean.y; g_xyz.z += sh_dmean.z;
+			gm[0] = ((clamp_bits >> 0) & 1u) ? 0.f : dL_dcolor.x;
+			gm[1] = ((clamp_bits >> 1) & 1u) ? 0.f : dL_dcolor.y;
+			gm[2] = ((clamp_bits >> 2) & 1u) ? 0.f : dL_dcolor.z;
 		}
-		for (int e = visible ? nact : 0; e < REST; e++) {
-			if (ADAM) adam1(rp[e], rm[e], rv[e], 0.f, h.lr[2], ac);
-			else rm[e] = 0.f;
-		}
-		// ---- the 14 remaining parameters
+		const int ncoef = (h.D + 1) * (h.D + 1);
+#pragma unroll
+		for (int k = 0; k < 16; k++) s_w[tid][k] = (k < ncoef) ? w[k] : 0.f;
+		s_g[tid][0] = gm[0]; s_g[tid][1] = gm[1]; s_g[tid][2] = gm[2];
+	}
+
+	// ---- the 14 small parameters of this Gaussian
+	if (valid) {
 		if (ADAM) {
-			float gx[3] = {g_xyz.x, g_xyz.y, g_xyz.z}, gd[3] = {g_dc.x, g_dc.y, g_dc.z}, gs[3] = {g_scale.x, g_scale.y, g_scale.z};
+			const float gx[3] = {g_xyz.x, g_xyz.y, g_xyz.z}, gd[3] = {g_dc.x, g_dc.y, g_dc.z}, gs[3] = {g_scale.x, g_scale.y, g_scale.z};
 #pragma unroll
 			for (int c = 0; c < 3; c++) {
 				float p = t.p[0][3 * idx + c], m = t.m[0][3 * idx + c], v = t.v[0][3 * idx + c];
-				adam1(p, m, v, gx[c], h.lr[0], ac);
+				adam1(p, m, v, gx[c], h.lr[0] * ac.inv_bc1, ac);
 				t.p[0][3 * idx + c] = p; t.m[0][3 * idx + c] = m; t.v[0][3 * idx + c] = v;
 				p = t.p[1][3 * idx + c]; m = t.m[1][3 * idx + c]; v = t.v[1][3 * idx + c];
-				adam1(p, m, v, gd[c], h.lr[1], ac);
+				adam1(p, m, v, gd[c], h.lr[1] * ac.inv_bc1, ac);
 				t.p[1][3 * idx + c] = p; t.m[1][3 * idx + c] = m; t.v[1][3 * idx + c] = v;
 				p = t.p[4][3 * idx + c]; m = t.m[4][3 * idx + c]; v = t.v[4][3 * idx + c];
-				adam1(p, m, v, gs[c], h.lr[4], ac);
+				adam1(p, m, v, gs[c], h.lr[4] * ac.inv_bc1, ac);
 				t.p[4][3 * idx + c] = p; t.m[4][3 * idx + c] = m; t.v[4][3 * idx + c] = v;
 			}
 			{
 				float p = t.p[3][idx], m = t.m[3][idx], v = t.v[3][idx];
-				adam1(p, m, v, g_opac, h.lr[3], ac);
+				adam1(p, m, v, g_opac, h.lr[3] * ac.inv_bc1, ac);
 				t.p[3][idx] = p; t.m[3][idx] = m; t.v[3][idx] = v;
 			}
 			{
 				float4 p = reinterpret_cast<float4*>(t.p[5])[idx], m = reinterpret_cast<float4*>(t.m[5])[idx], v = reinterpret_cast<float4*>(t.v[5])[idx];
-				adam1(p.x, m.x, v.x, g_rot.x, h.lr[5], ac);
-				adam1(p.y, m.y, v.y, g_rot.y, h.lr[5], ac);
-				adam1(p.z, m.z, v.z, g_rot.z, h.lr[5], ac);
-				adam1(p.w, m.w, v.w, g_rot.w, h.lr[5], ac);
+				const float lr = h.lr[5] * ac.inv_bc1;
+				adam1(p.x, m.x, v.x, g_rot.x, lr, ac);
+				adam1(p.y, m.y, v.y, g_rot.y, lr, ac);
+				adam1(p.z, m.z, v.z, g_rot.z, lr, ac);
+				adam1(p.w, m.w, v.w, g_rot.w, lr, ac);
 				reinterpret_cast<float4*>(t.p[5])[idx] = p; reinterpret_cast<float4*>(t.m[5])[idx] = m; reinterpret_cast<float4*>(t.v[5])[idx] = v;
 			}
 		} else {
@@ -203,25 +208,45 @@ __global__ void __launch_bounds__(TB) fused_backward_kernel(int P, TrainTensors 
 			reinterpret_cast<float4*>(grads.g[5])[idx] = g_rot;
 		}
 	}
-
-	// ---- rows back to global memory through the async proxy
-	fence_proxy_async_smem();
 	__syncthreads();
-	if (tid == 0) {
+
+	// ---- phase 2: element-wise over the block's f_rest chunk, 128-bit coalesced
+	const int n_el = rows * REST;
+	const int n4 = n_el / 4;
+	const float lr_rest = h.lr[2] * ac.inv_bc1;
+	float4* __restrict__ gp = reinterpret_cast<float4*>(t.p[2] + goff);
+	float4* __restrict__ gm4 = ADAM ? reinterpret_cast<float4*>(t.m[2] + goff) : reinterpret_cast<float4*>(grads.g[2] + goff);
+	float4* __restrict__ gv = ADAM ? reinterpret_cast<float4*>(t.v[2] + goff) : nullptr;
+	auto grad_of = [&](int e) {
+		const int row = e / REST, c = e - row * REST;
+		const int k = c / 3 + 1, ch = c - (k - 1) * 3;
+		return s_w[row][k] * s_g[row][ch];
+	};
+#pragma unroll 3
+	for (int i = tid; i < n4; i += TB) {
+		const int e = 4 * i;
+		const float4 g4 = make_float4(grad_of(e), grad_of(e + 1), grad_of(e + 2), grad_of(e + 3));
 		if (ADAM) {
-			bulk_s2g(t.p[2] + goff, s_p, bulk_bytes);
-			bulk_s2g(t.m[2] + goff, s_m, bulk_bytes);
-			bulk_s2g(t.v[2] + goff, s_v, bulk_bytes);
+			float4 p = reinterpret_cast<const float4*>(s_p)[i];
+			float4 m = gm4[i], v = gv[i];
+			adam1(p.x, m.x, v.x, g4.x, lr_rest, ac);
+			adam1(p.y, m.y, v.y, g4.y, lr_rest, ac);
+			adam1(p.z, m.z, v.z, g4.z, lr_rest, ac);
+			adam1(p.w, m.w, v.w, g4.w, lr_rest, ac);
+			gp[i] = p; gm4[i] = m; gv[i] = v;
 		} else {
-			bulk_s2g(grads.g[2] + goff, s_m, bulk_bytes);
+			gm4[i] = g4;
 		}
-		bulk_commit();
-		for (int i = 0; i < rem_floats; i++) {
-			const int o = bulk_bytes / 4 + i;
-			if (ADAM) { t.p[2][goff + o] = s_p[o]; t.m[2][goff + o] = s_m[o]; t.v[2][goff + o] = s_v[o]; }
-			else grads.g[2][goff + o] = s_m[o];
+	}
+	for (int e = 4 * n4 + tid; e < n_el; e += TB) {  // < 4 trailing elements of the last block
+		const float g = grad_of(e);
+		if (ADAM) {
+			float p = s_p[e], m = t.m[2][goff + e], v = t.v[2][goff + e];
+			adam1(p, m, v, g, lr_rest, ac);
+			t.p[2][goff + e] = p; t.m[2][goff + e] = m; t.v[2][goff + e] = v;
+		} else {
+			grads.g[2][goff + e] = g;
 		}
-		bulk_wait_read0();  // shared memory must stay alive until the TMA engine has read it
 	}
 }
 
@@ -233,37 +258,32 @@ __global__ void __launch_bounds__(256) adam_kernel(size_t n4, float4* __restrict
 	if (i >= n4) return;
 	float4 pp = p[i], mm = m[i], vv = v[i];
 	const float4 gg = g[i];
-	adam1(pp.x, mm.x, vv.x, gg.x * grad_scale, lr, c);
-	adam1(pp.y, mm.y, vv.y, gg.y * grad_scale, lr, c);
-	adam1(pp.z, mm.z, vv.z, gg.z * grad_scale, lr, c);
-	adam1(pp.w, mm.w, vv.w, gg.w * grad_scale, lr, c);
+	const float le = lr * c.inv_bc1;
+	adam1(pp.x, mm.x, vv.x, gg.x * grad_scale, le, c);
+	adam1(pp.y, mm.y, vv.y, gg.y * grad_scale, le, c);
+	adam1(pp.z, mm.z, vv.z, gg.z * grad_scale, le, c);
+	adam1(pp.w, mm.w, vv.w, gg.w * grad_scale, le, c);
 	p[i] = pp; m[i] = mm; v[i] = vv;
 }
 __global__ void adam_tail_kernel(size_t start, size_t n, float* p, float* m, float* v, const float* g, float lr, AdamCoef c, float grad_scale)
 {
 	const size_t i = start + threadIdx.x;
-	if (i < n) adam1(p[i], m[i], v[i], g[i] * grad_scale, lr, c);
+	if (i < n) adam1(p[i], m[i], v[i], g[i] * grad_scale, lr * c.inv_bc1, c);
 }
 
 }  // namespace
 
-size_t fused_backward_smem_bytes(bool adam) { return (size_t)(adam ? 3 : 2) * TB * REST * sizeof(float); }
+size_t fused_backward_smem_bytes(bool) { return 0; }  // static shared memory only
 
 int launch_fused_backward(bool adam, int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, const StepHyper& h,
                           const GradSegments& grads, const DensifyStats& st, const uint32_t* counters, uint32_t capacity, cudaStream_t stream)
 {
 	if (P == 0) return 0;
-	static bool attr_set = false;
-	if (!attr_set) {
-		PSB_CUDA_OK(cudaFuncSetAttribute(fused_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_backward_smem_bytes(true)));
-		PSB_CUDA_OK(cudaFuncSetAttribute(fused_backward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_backward_smem_bytes(false)));
-		attr_set = true;
-	}
 	const int grid = cdiv(P, TB);
 	if (adam)
-		fused_backward_kernel<true><<<grid, TB, fused_backward_smem_bytes(true), stream>>>(P, t, cam, geom, reinterpret_cast<float4*>(sink), h, grads, st, counters, capacity);
+		fused_backward_kernel<true><<<grid, TB, 0, stream>>>(P, t, cam, geom, reinterpret_cast<float4*>(sink), h, grads, st, counters, capacity);
 	else
-		fused_backward_kernel<false><<<grid, TB, fused_backward_smem_bytes(false), stream>>>(P, t, cam, geom, reinterpret_cast<float4*>(sink), h, grads, st, counters, capacity);
+		fused_backward_kernel<false><<<grid, TB, 0, stream>>>(P, t, cam, geom, reinterpret_cast<float4*>(sink), h, grads, st, counters, capacity);
 	PSB_LAUNCH_OK();
 	return 0;
 }
@@ -272,7 +292,7 @@ int launch_adam(size_t n, float* p, float* m, float* v, const float* g, float lr
 {
 	if (n == 0) return 0;
 	AdamCoef c;
-	c.beta1 = h.beta1; c.beta2 = h.beta2; c.eps = h.eps; c.inv_bc1 = h.inv_bc1; c.bc2_sqrt = h.bc2_sqrt;
+	c.beta1 = h.beta1; c.beta2 = h.beta2; c.eps = h.eps; c.inv_bc1 = h.inv_bc1; c.inv_bc2_sqrt = 1.0f / h.bc2_sqrt;
 	const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(g)) & 15) == 0;
 	const size_t n4 = aligned ? n / 4 : 0;
 	if (n4) {

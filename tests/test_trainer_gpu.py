@@ -100,8 +100,10 @@ def test_adam_update_matches_torch_adam(cuda):
         _lib.check(tr.L.psb_adam_update(P, 16, C.byref(cm), ptrs, C.byref(cs), 1.0, None), "adam")
         model.step_ += 1
         torch.cuda.synchronize()
-        for p, t in zip(params, model.tensors()):
-            assert torch.allclose(t, p.detach(), rtol=3e-6, atol=1e-9), it
+        # the update direction m / (sqrt(v) + eps) is O(1): agreement is measured in units of one step (lr);
+        # psb200 evaluates sqrt / division on the MUFU unit (~2 ulp), torch with IEEE sequences
+        for p, t, lrate in zip(params, model.tensors(), LRS):
+            assert (t - p.detach()).abs().max().item() <= 2e-5 * lrate + 1e-6 * p.detach().abs().max().item(), it
 
 
 def test_fused_step_equals_split_path_and_tracks_reference(cuda):
