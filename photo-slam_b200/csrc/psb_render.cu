@@ -114,6 +114,9 @@ __global__ void __launch_bounds__(RB) render_fwd_kernel(const uint2* __restrict_
 	const float2 pixf = make_float2((float)px, (float)py);
 	const float rx0 = (float)tile_x0, ry0 = (float)tile_y0;
 	const float rx1 = (float)(min(tile_x0 + PSB_TILE_X, W) - 1), ry1 = (float)(min(tile_y0 + PSB_TILE_Y, H) - 1);
+	// pixel rectangle of this warp's 8x4 footprint (clamped to the image; degenerate if the warp is outside)
+	const float wx0 = (float)(tile_x0 + (warp & 1) * 8), wy0 = (float)(tile_y0 + (warp >> 1) * 4);
+	const float wx1 = fmaxf(wx0, fminf(wx0 + 7.f, (float)(W - 1))), wy1 = fmaxf(wy0, fminf(wy0 + 3.f, (float)(H - 1)));
 
 	const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
 	const int n = (int)(range.y - range.x);
@@ -143,25 +146,41 @@ __global__ void __launch_bounds__(RB) render_fwd_kernel(const uint2* __restrict_
 		if (tid < cnt) keep = splat_reaches_tile(s_rec[st][tid].q0, s_rec[st][tid].q1, rx0, ry0, rx1, ry1);
 		const int ccount = compact_block(keep, s_cidx, s_wcnt, tid);
 
-		for (int k = 0; !done && k < ccount; k++) {
-			const int j = s_cidx[k];
-			const float4 q0 = s_rec[st][j].q0;
-			const float4 q1 = s_rec[st][j].q1;
-			const float2 xy = make_float2(q0.x, q0.y);
-			const float2 d = make_float2(xy.x - pixf.x, xy.y - pixf.y);
-			const float4 con_o = make_float4(q0.z, q0.w, q1.x, q1.y);
-			const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-			if (power > 0.0f) continue;
-			const float alpha = min(0.99f, con_o.w * exp(power));
-			if (alpha < 1.0f / 255.0f) continue;
-			const float test_T = T * (1 - alpha);
-			if (test_T < 0.0001f) { done = true; continue; }
-			const float cb = s_rec[st][j].q2.x;
-			C[0] += q1.z * alpha * T;
-			C[1] += q1.w * alpha * T;
-			C[2] += cb * alpha * T;
-			T = test_T;
-			last_contributor = (uint32_t)(b * RB + j + 1);
+		// Second, per-warp cull: each lane tests one surviving entry against this warp's 8x4 pixel footprint
+		// (32 entries per ballot), then the warp walks only the entries that can reach one of its pixels.
+		for (int c0 = 0; c0 < ccount; c0 += 32) {
+			if (__all_sync(0xffffffffu, done)) break;
+			const int kk = c0 + lane;
+			int j = 0;
+			bool hit = false;
+			if (kk < ccount) {
+				j = s_cidx[kk];
+				hit = splat_reaches_tile(s_rec[st][j].q0, s_rec[st][j].q1, wx0, wy0, wx1, wy1);
+			}
+			uint32_t hits = __ballot_sync(0xffffffffu, hit);
+			while (hits) {
+				const int src = __ffs(hits) - 1;
+				hits &= hits - 1;
+				const int jj = __shfl_sync(0xffffffffu, j, src);
+				if (done) continue;
+				const float4 q0 = s_rec[st][jj].q0;
+				const float4 q1 = s_rec[st][jj].q1;
+				const float2 xy = make_float2(q0.x, q0.y);
+				const float2 d = make_float2(xy.x - pixf.x, xy.y - pixf.y);
+				const float4 con_o = make_float4(q0.z, q0.w, q1.x, q1.y);
+				const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+				if (power > 0.0f) continue;
+				const float alpha = min(0.99f, con_o.w * exp(power));
+				if (alpha < 1.0f / 255.0f) continue;
+				const float test_T = T * (1 - alpha);
+				if (test_T < 0.0001f) { done = true; continue; }
+				const float cb = s_rec[st][jj].q2.x;
+				C[0] += q1.z * alpha * T;
+				C[1] += q1.w * alpha * T;
+				C[2] += cb * alpha * T;
+				T = test_T;
+				last_contributor = (uint32_t)(b * RB + jj + 1);
+			}
 		}
 	}
 
@@ -253,6 +272,9 @@ __global__ void __launch_bounds__(RB) render_bwd_kernel(const uint2* __restrict_
 	const float2 pixf = make_float2((float)px, (float)py);
 	const float rx0 = (float)tile_x0, ry0 = (float)tile_y0;
 	const float rx1 = (float)(min(tile_x0 + PSB_TILE_X, W) - 1), ry1 = (float)(min(tile_y0 + PSB_TILE_Y, H) - 1);
+	// pixel rectangle of this warp's 8x4 footprint (clamped to the image; degenerate if the warp is outside)
+	const float wx0 = (float)(tile_x0 + (warp & 1) * 8), wy0 = (float)(tile_y0 + (warp >> 1) * 4);
+	const float wx1 = fmaxf(wx0, fminf(wx0 + 7.f, (float)(W - 1))), wy1 = fmaxf(wy0, fminf(wy0 + 3.f, (float)(H - 1)));
 
 	const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
 
@@ -262,6 +284,7 @@ __global__ void __launch_bounds__(RB) render_bwd_kernel(const uint2* __restrict_
 
 	// Nothing behind the deepest last contributor of the tile can receive gradient: start there.
 	int maxc = __reduce_max_sync(0xffffffffu, last_contributor);
+	const int warp_maxc = maxc;
 	if (lane == 0) sm.wcnt[warp] = maxc;
 	if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); mbar_fence_init(); }
 	if (tid < RBB) sm.dirty[tid] = 0ull;
@@ -313,8 +336,20 @@ __global__ void __launch_bounds__(RB) render_bwd_kernel(const uint2* __restrict_
 		if (tid < cnt) keep = splat_reaches_tile(sm.rec[st][tid].q0, sm.rec[st][tid].q1, rx0, ry0, rx1, ry1);
 		const int ccount = compact_block(keep, sm.cidx, sm.wcnt, tid);
 
-		for (int k = 0; k < ccount; k++) {
-			const int j = sm.cidx[k];
+		for (int c0 = 0; c0 < ccount; c0 += 32) {
+		const int kk = c0 + lane;
+		int jl = 0;
+		bool hit = false;
+		if (kk < ccount) {
+			jl = sm.cidx[kk];
+			// entries behind every pixel's last contributor of this warp cannot receive gradient either
+			hit = (n - 1 - (b * RBB + jl)) < warp_maxc && splat_reaches_tile(sm.rec[st][jl].q0, sm.rec[st][jl].q1, wx0, wy0, wx1, wy1);
+		}
+		uint32_t hits = __ballot_sync(0xffffffffu, hit);
+		while (hits) {
+			const int src = __ffs(hits) - 1;
+			hits &= hits - 1;
+			const int j = __shfl_sync(0xffffffffu, jl, src);
 			// 0-based list position of this entry; the reference's `contributor` after its decrement
 			const int pos = n - 1 - (b * RBB + j);
 			bool active = pos < last_contributor;
@@ -370,6 +405,7 @@ __global__ void __launch_bounds__(RB) render_bwd_kernel(const uint2* __restrict_
 			// each (warp, entry) pair is visited once per batch: plain stores, no shared-memory atomics
 			if (my_slot >= 0) sm.acc[j * ACC_ROW + warp * 9 + my_slot] = tot;
 			if (lane == 0) dirty8[j * 8 + warp] = 1;
+		}
 		}
 		__syncthreads();
 
