@@ -55,12 +55,12 @@ __global__ void export_geom_kernel(int P, GeomState geom, float* depths, float* 
 	r.q0 = r.q1 = r.q2 = make_float4(0, 0, 0, 0);
 	if (tt) r = geom.rec[i];
 	if (tiles_touched) tiles_touched[i] = tt;
-	if (depths) depths[i] = r.q2.y;
+	if (depths) depths[i] = r.q1.w;
 	if (means2D) { means2D[2 * i] = r.q0.x; means2D[2 * i + 1] = r.q0.y; }
 	if (conic_opacity) { conic_opacity[4 * i] = r.q0.z; conic_opacity[4 * i + 1] = r.q0.w; conic_opacity[4 * i + 2] = r.q1.x; conic_opacity[4 * i + 3] = r.q1.y; }
-	if (rgb) { rgb[3 * i] = r.q1.z; rgb[3 * i + 1] = r.q1.w; rgb[3 * i + 2] = r.q2.x; }
+	if (rgb) { rgb[3 * i] = r.q2.x; rgb[3 * i + 1] = r.q2.y; rgb[3 * i + 2] = r.q2.z; }
 	if (clamped) {
-		const uint32_t cb = __float_as_uint(r.q2.w);
+		const uint32_t cb = rec_clamp_bits(__float_as_uint(r.q2.w));
 		clamped[3 * i] = cb & 1u; clamped[3 * i + 1] = (cb >> 1) & 1u; clamped[3 * i + 2] = (cb >> 2) & 1u;
 	}
 }
@@ -69,7 +69,7 @@ __global__ void export_keys_kernel(int R, const uint32_t* tile_key, const uint32
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= R) return;
 	const uint32_t g = inst[i];
-	if (keys) keys[i] = ((uint64_t)tile_key[i] << 32) | (uint64_t)__float_as_uint(rec[g].q2.y);
+	if (keys) keys[i] = ((uint64_t)tile_key[i] << 32) | (uint64_t)__float_as_uint(rec[g].q1.w);
 	if (values) values[i] = g;
 }
 

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(GaussIn in, Camera 
 		rot = reinterpret_cast<const float4*>(in.rotations)[idx];
 		cov3d_from_scale_rot(scale, in.scale_modifier, rot, cov3D);
 	}
-	const uint32_t clamp_bits = __float_as_uint(geom.rec[idx].q2.w);
+	const uint32_t clamp_bits = rec_clamp_bits(__float_as_uint(geom.rec[idx].q2.w));
 	const float2 g2 = make_float2(dL_dmean2D[(size_t)idx * mean2D_stride], dL_dmean2D[(size_t)idx * mean2D_stride + 1]);
 	const float3 gc = make_float3(dL_dconic[(size_t)idx * conic_stride], dL_dconic[(size_t)idx * conic_stride + 1],
 	                              dL_dconic[(size_t)idx * conic_stride + 3]);

@@ -41,13 +41,18 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // Per-Gaussian screen-space record produced by the forward preprocess and consumed (as one
 // 48-byte bulk copy) by the tile kernels. 16-byte aligned, three float4 lanes:
 //   q0 = (mean2D.x, mean2D.y, conic.a, conic.b)
-//   q1 = (conic.c,  opacity,  rgb.r,   rgb.g)
-//   q2 = (rgb.b,    depth,    radius (int bits), flags (bit0..2 = SH clamp per channel))
+//   q1 = (conic.c,  opacity,  pmin,    depth)      pmin = -(ln(255 * opacity) + 1e-3): a pixel whose exponent
+//                                                   `power` is below pmin cannot reach alpha >= 1/255, so the tile
+//                                                   kernels skip exp() for it (the exact alpha test still decides
+//                                                   everything at or above pmin)
+//   q2 = (rgb.r,    rgb.g,    rgb.b,   meta)       meta bits: radius << 3 | SH clamp flag per channel (bits 0..2)
 // ---------------------------------------------------------------------------------------------
 struct __align__(16) GaussRec {
 	float4 q0, q1, q2;
 };
 static_assert(sizeof(GaussRec) == 48, "GaussRec must be 48 bytes");
+__host__ __device__ __forceinline__ int rec_radius(uint32_t meta) { return (int)(meta >> 3); }
+__host__ __device__ __forceinline__ uint32_t rec_clamp_bits(uint32_t meta) { return meta & 7u; }
 
 // Camera block passed by value to the per-Gaussian kernels. The 4x4 matrices stay where the caller put
 // them (device memory, column-major m[4*c + r] exactly as the reference passes them, e.g.

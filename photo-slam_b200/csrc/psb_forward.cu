@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(128) preprocess_fwd_kernel(GaussIn in, Camera 
 	const int radius_i = (int)my_radius;
 	GaussRec r;
 	r.q0 = make_float4(point_image.x, point_image.y, conic.x, conic.y);
-	r.q1 = make_float4(conic.z, opacity, rgb.x, rgb.y);
-	r.q2 = make_float4(rgb.z, p_view.z, __int_as_float(radius_i), __uint_as_float(clamp_bits));
+	r.q1 = make_float4(conic.z, opacity, -(__logf(255.0f * opacity) + 1e-3f), p_view.z);
+	r.q2 = make_float4(rgb.x, rgb.y, rgb.z, __uint_as_float(((uint32_t)radius_i << 3) | clamp_bits));
 	geom.rec[idx] = r;
 	geom.depth_key[0][idx] = __float_as_uint(p_view.z);
 	if (radii_out) radii_out[idx] = radius_i;

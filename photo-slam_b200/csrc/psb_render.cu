@@ -170,14 +170,15 @@ __global__ void __launch_bounds__(RB) render_fwd_kernel(const uint2* __restrict_
 				const float4 con_o = make_float4(q0.z, q0.w, q1.x, q1.y);
 				const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
 				if (power > 0.0f) continue;
+				if (power < q1.z) continue;  // below pmin: alpha < 1/255 for certain, skip exp (see GaussRec)
 				const float alpha = min(0.99f, con_o.w * exp(power));
 				if (alpha < 1.0f / 255.0f) continue;
 				const float test_T = T * (1 - alpha);
 				if (test_T < 0.0001f) { done = true; continue; }
-				const float cb = s_rec[st][jj].q2.x;
-				C[0] += q1.z * alpha * T;
-				C[1] += q1.w * alpha * T;
-				C[2] += cb * alpha * T;
+				const float4 q2 = s_rec[st][jj].q2;
+				C[0] += q2.x * alpha * T;
+				C[1] += q2.y * alpha * T;
+				C[2] += q2.z * alpha * T;
 				T = test_T;
 				last_contributor = (uint32_t)(b * RB + jj + 1);
 			}
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(RB) render_bwd_kernel(const uint2* __restrict_
 			const float2 d = make_float2(xy.x - pixf.x, xy.y - pixf.y);
 			const float4 con_o = make_float4(q0.z, q0.w, q1.x, q1.y);
 			const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-			active = active && !(power > 0.0f);
+			active = active && !(power > 0.0f) && !(power < q1.z);  // q1.z = pmin, see GaussRec
 			float G = 0.f, alpha = 0.f;
 			if (active) {
 				G = exp(power);
@@ -374,7 +375,8 @@ __global__ void __launch_bounds__(RB) render_bwd_kernel(const uint2* __restrict_
 			if (active) {
 				T = T / (1.f - alpha);
 				const float dchannel_dcolor = alpha * T;
-				const float col[3] = {q1.z, q1.w, sm.rec[st][j].q2.x};
+				const float4 q2 = sm.rec[st][j].q2;
+				const float col[3] = {q2.x, q2.y, q2.z};
 				float dL_dalpha = 0.0f;
 #pragma unroll
 				for (int ch = 0; ch < 3; ch++) {

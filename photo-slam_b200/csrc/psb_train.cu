@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(TB) fused_backward_kernel(int P, TrainTensors 
 		bulk_g2s(s_p, t.p[2] + goff, bulk_bytes, &s_bar);
 		for (int i = 0; i < rem_floats; i++) s_p[bulk_bytes / 4 + i] = t.p[2][goff + bulk_bytes / 4 + i];  // < 16 trailing bytes (last block)
 	}
+	__syncthreads();  // the mbarrier must be initialised before any other thread waits on it
 
 	const int idx = base + tid;
 	const bool valid = idx < P;
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(TB) fused_backward_kernel(int P, TrainTensors 
 			const float4 qraw = reinterpret_cast<const float4*>(t.p[5])[idx];
 			const float oraw = t.p[3][idx];
 			const float4 rq2 = geom.rec[idx].q2;
-			clamp_bits = __float_as_uint(rq2.w);
+			clamp_bits = rec_clamp_bits(__float_as_uint(rq2.w));
 			// activations exactly as in the forward (preprocess_fwd_kernel<RAW>)
 			const float3 s = make_float3(expf(sraw.x), expf(sraw.y), expf(sraw.z));
 			const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(TB) fused_backward_kernel(int P, TrainTensors 
 			g_rot = make_float4((dL_drot.x - q.x * qd) / qn, (dL_drot.y - q.y * qd) / qn, (dL_drot.z - q.z * qd) / qn, (dL_drot.w - q.w * qd) / qn);
 			g_opac = dL_dopacity * sig * (1.0f - sig);
 			if (st.enabled) {
-				st.max_radii2D[idx] = fmaxf(st.max_radii2D[idx], (float)__float_as_int(rq2.z));
+				st.max_radii2D[idx] = fmaxf(st.max_radii2D[idx], (float)rec_radius(__float_as_uint(rq2.w)));
 				st.xyz_gradient_accum[idx] += sqrtf(dL_dmean2D.x * dL_dmean2D.x + dL_dmean2D.y * dL_dmean2D.y);
 				st.denom[idx] += 1.0f;
 			}

@@ -98,6 +98,8 @@ CONFIGS = [
     (20_000, "euroc", None, 5, 2, (0.2, 0.5, 0.7), 4.0),
     (5_000, "tum", (203, 117), 7, 1, (1.0, 1.0, 1.0), 6.0),
     (3_000, "tum", (64, 48), 9, 0, (0.0, 0.0, 0.0), 12.0),
+    # long tile lists (~2500 entries/tile): many staging batches, early termination of saturated tiles
+    (150_000, "tum", (320, 240), 11, 3, (0.0, 0.0, 0.0), 2.4),
 ]
 
 
