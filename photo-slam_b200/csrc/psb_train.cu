@@ -57,7 +57,7 @@ __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, flo
 // bulk copy per block. Phase 2 (whole block, element-wise, 128-bit coalesced): Adam over the block's
 // [128 x 45] f_rest chunk, gradient looked up from the seeds in shared memory.
 template <bool ADAM>
-__global__ void __launch_bounds__(TB) fused_backward_kernel(int P, TrainTensors t, Camera cam, GeomState geom, float4* __restrict__ sink,
+__global__ void __launch_bounds__(TB, 5) fused_backward_kernel(int P, TrainTensors t, Camera cam, GeomState geom, float4* __restrict__ sink,
                                                             StepHyper h, GradSegments grads, DensifyStats st,
                                                             const uint32_t* __restrict__ counters, uint32_t capacity)
 {
@@ -100,9 +100,19 @@ __global__ void __launch_bounds__(TB) fused_backward_kernel(int P, TrainTensors 
 	float3 mean = make_float3(0, 0, 1), dc = make_float3(0, 0, 0);
 	float3 dL_dcolor = make_float3(0, 0, 0);
 	uint32_t clamp_bits = 0;
+	// the 14 small parameters (every Gaussian needs them for its Adam update): issued up front, with the
+	// screen-space sums, as one batch of independent loads — a single memory round trip instead of a chain
+	float sp_xyz[3] = {0, 0, 1}, sp_dc[3] = {0, 0, 0}, sp_sc[3] = {0, 0, 0}, sp_op = 0.f;
+	float4 sp_rot = make_float4(1, 0, 0, 0);
 	if (valid) {
-		visible = geom.tiles_touched[idx] != 0;
+		const uint32_t tt = geom.tiles_touched[idx];
 		const float4 s0 = sink[3 * idx], s1 = sink[3 * idx + 1], s2 = sink[3 * idx + 2];
+		const uint32_t meta = __float_as_uint(geom.rec[idx].q2.w);
+#pragma unroll
+		for (int c = 0; c < 3; c++) { sp_xyz[c] = t.p[0][3 * idx + c]; sp_dc[c] = t.p[1][3 * idx + c]; sp_sc[c] = t.p[4][3 * idx + c]; }
+		sp_op = t.p[3][idx];
+		sp_rot = reinterpret_cast<const float4*>(t.p[5])[idx];
+		visible = tt != 0;
 		const float4 z = make_float4(0, 0, 0, 0);
 		sink[3 * idx] = z; sink[3 * idx + 1] = z; sink[3 * idx + 2] = z;  // ready for the next iteration
 		if (visible) {
@@ -111,13 +121,12 @@ __global__ void __launch_bounds__(TB) fused_backward_kernel(int P, TrainTensors 
 			const float3 dL_dconic = make_float3(s0.w, s1.x, s1.z);
 			const float dL_dopacity = s1.w;
 			dL_dcolor = make_float3(s2.x, s2.y, s2.z);
-			mean = make_float3(t.p[0][3 * idx], t.p[0][3 * idx + 1], t.p[0][3 * idx + 2]);
-			dc = make_float3(t.p[1][3 * idx], t.p[1][3 * idx + 1], t.p[1][3 * idx + 2]);
-			const float3 sraw = make_float3(t.p[4][3 * idx], t.p[4][3 * idx + 1], t.p[4][3 * idx + 2]);
-			const float4 qraw = reinterpret_cast<const float4*>(t.p[5])[idx];
-			const float oraw = t.p[3][idx];
-			const float4 rq2 = geom.rec[idx].q2;
-			clamp_bits = rec_clamp_bits(__float_as_uint(rq2.w));
+			mean = make_float3(sp_xyz[0], sp_xyz[1], sp_xyz[2]);
+			dc = make_float3(sp_dc[0], sp_dc[1], sp_dc[2]);
+			const float3 sraw = make_float3(sp_sc[0], sp_sc[1], sp_sc[2]);
+			const float4 qraw = sp_rot;
+			const float oraw = sp_op;
+			clamp_bits = rec_clamp_bits(meta);
 			// activations exactly as in the forward (preprocess_fwd_kernel<RAW>)
 			const float3 s = make_float3(expf(sraw.x), expf(sraw.y), expf(sraw.z));
 			const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
@@ -135,7 +144,7 @@ __global__ void __launch_bounds__(TB) fused_backward_kernel(int P, TrainTensors 
 			g_rot = make_float4((dL_drot.x - q.x * qd) / qn, (dL_drot.y - q.y * qd) / qn, (dL_drot.z - q.z * qd) / qn, (dL_drot.w - q.w * qd) / qn);
 			g_opac = dL_dopacity * sig * (1.0f - sig);
 			if (st.enabled) {
-				st.max_radii2D[idx] = fmaxf(st.max_radii2D[idx], (float)rec_radius(__float_as_uint(rq2.w)));
+				st.max_radii2D[idx] = fmaxf(st.max_radii2D[idx], (float)rec_radius(meta));
 				st.xyz_gradient_accum[idx] += sqrtf(dL_dmean2D.x * dL_dmean2D.x + dL_dmean2D.y * dL_dmean2D.y);
 				st.denom[idx] += 1.0f;
 			}
@@ -174,33 +183,36 @@ __global__ void __launch_bounds__(TB) fused_backward_kernel(int P, TrainTensors 
 	// ---- the 14 small parameters of this Gaussian
 	if (valid) {
 		if (ADAM) {
+			// load every moment first (independent loads, one round trip), then update, then store
+			float m3[3][3], v3[3][3], mo, vo;
+			const int tsel[3] = {0, 1, 4};
+#pragma unroll
+			for (int a = 0; a < 3; a++)
+#pragma unroll
+				for (int c = 0; c < 3; c++) { m3[a][c] = t.m[tsel[a]][3 * idx + c]; v3[a][c] = t.v[tsel[a]][3 * idx + c]; }
+			mo = t.m[3][idx]; vo = t.v[3][idx];
+			float4 mr = reinterpret_cast<const float4*>(t.m[5])[idx], vr = reinterpret_cast<const float4*>(t.v[5])[idx];
 			const float gx[3] = {g_xyz.x, g_xyz.y, g_xyz.z}, gd[3] = {g_dc.x, g_dc.y, g_dc.z}, gs[3] = {g_scale.x, g_scale.y, g_scale.z};
 #pragma unroll
 			for (int c = 0; c < 3; c++) {
-				float p = t.p[0][3 * idx + c], m = t.m[0][3 * idx + c], v = t.v[0][3 * idx + c];
-				adam1(p, m, v, gx[c], h.lr[0] * ac.inv_bc1, ac);
-				t.p[0][3 * idx + c] = p; t.m[0][3 * idx + c] = m; t.v[0][3 * idx + c] = v;
-				p = t.p[1][3 * idx + c]; m = t.m[1][3 * idx + c]; v = t.v[1][3 * idx + c];
-				adam1(p, m, v, gd[c], h.lr[1] * ac.inv_bc1, ac);
-				t.p[1][3 * idx + c] = p; t.m[1][3 * idx + c] = m; t.v[1][3 * idx + c] = v;
-				p = t.p[4][3 * idx + c]; m = t.m[4][3 * idx + c]; v = t.v[4][3 * idx + c];
-				adam1(p, m, v, gs[c], h.lr[4] * ac.inv_bc1, ac);
-				t.p[4][3 * idx + c] = p; t.m[4][3 * idx + c] = m; t.v[4][3 * idx + c] = v;
+				adam1(sp_xyz[c], m3[0][c], v3[0][c], gx[c], h.lr[0] * ac.inv_bc1, ac);
+				adam1(sp_dc[c], m3[1][c], v3[1][c], gd[c], h.lr[1] * ac.inv_bc1, ac);
+				adam1(sp_sc[c], m3[2][c], v3[2][c], gs[c], h.lr[4] * ac.inv_bc1, ac);
 			}
-			{
-				float p = t.p[3][idx], m = t.m[3][idx], v = t.v[3][idx];
-				adam1(p, m, v, g_opac, h.lr[3] * ac.inv_bc1, ac);
-				t.p[3][idx] = p; t.m[3][idx] = m; t.v[3][idx] = v;
+			adam1(sp_op, mo, vo, g_opac, h.lr[3] * ac.inv_bc1, ac);
+			const float lrr = h.lr[5] * ac.inv_bc1;
+			adam1(sp_rot.x, mr.x, vr.x, g_rot.x, lrr, ac);
+			adam1(sp_rot.y, mr.y, vr.y, g_rot.y, lrr, ac);
+			adam1(sp_rot.z, mr.z, vr.z, g_rot.z, lrr, ac);
+			adam1(sp_rot.w, mr.w, vr.w, g_rot.w, lrr, ac);
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				t.p[0][3 * idx + c] = sp_xyz[c]; t.m[0][3 * idx + c] = m3[0][c]; t.v[0][3 * idx + c] = v3[0][c];
+				t.p[1][3 * idx + c] = sp_dc[c]; t.m[1][3 * idx + c] = m3[1][c]; t.v[1][3 * idx + c] = v3[1][c];
+				t.p[4][3 * idx + c] = sp_sc[c]; t.m[4][3 * idx + c] = m3[2][c]; t.v[4][3 * idx + c] = v3[2][c];
 			}
-			{
-				float4 p = reinterpret_cast<float4*>(t.p[5])[idx], m = reinterpret_cast<float4*>(t.m[5])[idx], v = reinterpret_cast<float4*>(t.v[5])[idx];
-				const float lr = h.lr[5] * ac.inv_bc1;
-				adam1(p.x, m.x, v.x, g_rot.x, lr, ac);
-				adam1(p.y, m.y, v.y, g_rot.y, lr, ac);
-				adam1(p.z, m.z, v.z, g_rot.z, lr, ac);
-				adam1(p.w, m.w, v.w, g_rot.w, lr, ac);
-				reinterpret_cast<float4*>(t.p[5])[idx] = p; reinterpret_cast<float4*>(t.m[5])[idx] = m; reinterpret_cast<float4*>(t.v[5])[idx] = v;
-			}
+			t.p[3][idx] = sp_op; t.m[3][idx] = mo; t.v[3][idx] = vo;
+			reinterpret_cast<float4*>(t.p[5])[idx] = sp_rot; reinterpret_cast<float4*>(t.m[5])[idx] = mr; reinterpret_cast<float4*>(t.v[5])[idx] = vr;
 		} else {
 			grads.g[0][3 * idx] = g_xyz.x; grads.g[0][3 * idx + 1] = g_xyz.y; grads.g[0][3 * idx + 2] = g_xyz.z;
 			grads.g[1][3 * idx] = g_dc.x; grads.g[1][3 * idx + 1] = g_dc.y; grads.g[1][3 * idx + 2] = g_dc.z;
@@ -223,20 +235,32 @@ __global__ void __launch_bounds__(TB) fused_backward_kernel(int P, TrainTensors 
 		const int k = c / 3 + 1, ch = c - (k - 1) * 3;
 		return s_w[row][k] * s_g[row][ch];
 	};
-#pragma unroll 3
-	for (int i = tid; i < n4; i += TB) {
-		const int e = 4 * i;
-		const float4 g4 = make_float4(grad_of(e), grad_of(e + 1), grad_of(e + 2), grad_of(e + 3));
+	constexpr int PF = 4;  // float4 groups in flight per thread and tensor
+	for (int i0 = tid; i0 < n4; i0 += PF * TB) {
+		float4 m[PF], v[PF];
 		if (ADAM) {
-			float4 p = reinterpret_cast<const float4*>(s_p)[i];
-			float4 m = gm4[i], v = gv[i];
-			adam1(p.x, m.x, v.x, g4.x, lr_rest, ac);
-			adam1(p.y, m.y, v.y, g4.y, lr_rest, ac);
-			adam1(p.z, m.z, v.z, g4.z, lr_rest, ac);
-			adam1(p.w, m.w, v.w, g4.w, lr_rest, ac);
-			gp[i] = p; gm4[i] = m; gv[i] = v;
-		} else {
-			gm4[i] = g4;
+#pragma unroll
+			for (int u = 0; u < PF; u++) {
+				const int i = i0 + u * TB;
+				if (i < n4) { m[u] = gm4[i]; v[u] = gv[i]; }
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < PF; u++) {
+			const int i = i0 + u * TB;
+			if (i >= n4) break;
+			const int e = 4 * i;
+			const float4 g4 = make_float4(grad_of(e), grad_of(e + 1), grad_of(e + 2), grad_of(e + 3));
+			if (ADAM) {
+				float4 p = reinterpret_cast<const float4*>(s_p)[i];
+				adam1(p.x, m[u].x, v[u].x, g4.x, lr_rest, ac);
+				adam1(p.y, m[u].y, v[u].y, g4.y, lr_rest, ac);
+				adam1(p.z, m[u].z, v[u].z, g4.z, lr_rest, ac);
+				adam1(p.w, m[u].w, v[u].w, g4.w, lr_rest, ac);
+				gp[i] = p; gm4[i] = m[u]; gv[i] = v[u];
+			} else {
+				gm4[i] = g4;
+			}
 		}
 	}
 	for (int e = 4 * n4 + tid; e < n_el; e += TB) {  // < 4 trailing elements of the last block
