@@ -1,0 +1,50 @@
+"""Host-side logic of the keyframe-sharded data-parallel path. Device-agnostic (torch tensors on
+any device, any torch.distributed backend): exercised with gloo on CPU in tests/test_parallel_cpu.py and with NCCL
+on the B200s by trainer.DataParallelTrainer / bench.py --gpus N."""
+import torch
+
+SIZES = (3, 3, 45, 1, 3, 4)   # floats per Gaussian of xyz, features_dc, features_rest, opacity, scaling, rotation
+PER_GAUSSIAN = sum(SIZES)     # 59
+
+
+def shard_schedule(schedule, rank, world):
+    """Rank r consumes entries r, r+K, r+2K, ... of the shuffled keyframe schedule: K consecutive entries of the
+    reference's single-view schedule (gaussian_mapper.cpp:1126-1173) form one data-parallel step."""
+    usable = len(schedule) - len(schedule) % world
+    return list(schedule[rank:usable:world])
+
+
+class GradBuffer:
+    """ONE flat [P*59] float32 buffer with six views in the reference's tensor shapes, so the whole gradient of a
+    step is a single all-reduce call."""
+
+    def __init__(self, P, device):
+        self.P = P
+        self.flat = torch.zeros(P * PER_GAUSSIAN, dtype=torch.float32, device=device)
+        self.segments, o = [], 0
+        for s in SIZES:
+            self.segments.append(self.flat[o:o + P * s])
+            o += P * s
+
+    def views(self):
+        P = self.P
+        shapes = [(P, 3), (P, 1, 3), (P, 15, 3), (P, 1), (P, 3), (P, 4)]
+        return [seg.view(*sh) for seg, sh in zip(self.segments, shapes)]
+
+    def all_reduce(self, group=None):
+        """Sum over ranks; returns the factor the optimizer applies (mean over the K views of the step)."""
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        return 1.0 / world
+
+
+def reduce_densify_stats(max_radii2D, xyz_gradient_accum, denom, group=None):
+    """Called once, right before densify/prune: max over ranks for the radii, sum for the accumulators
+    (every rank then holds the statistics of all views seen since the last densification)."""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(max_radii2D, op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(xyz_gradient_accum, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(denom, op=dist.ReduceOp.SUM, group=group)

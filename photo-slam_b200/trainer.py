@@ -272,14 +272,9 @@ class DataParallelTrainer(GaussianTrainer):
         self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        P = model.num_points()
-        self.sizes = [3, 3, 45, 1, 3, 4]
-        self.flat = torch.zeros(P * 59, dtype=torch.float32, device=model.device)
-        offs, o = [], 0
-        for s in self.sizes:
-            offs.append(o)
-            o += P * s
-        self.segs = [self.flat[offs[i]: offs[i] + P * self.sizes[i]] for i in range(6)]
+        from .parallel import GradBuffer
+        self.grads = GradBuffer(model.num_points(), model.device)
+        self.flat, self.segs = self.grads.flat, self.grads.segments
 
     def trainForOneIteration(self, cam, gt_image, mask=None, out_color=None, radii=None, densify_stats=None):
         m = self.model
@@ -293,14 +288,16 @@ class DataParallelTrainer(GaussianTrainer):
                                                gt_image.data_ptr(), mask.data_ptr() if mask is not None else None, C.byref(cs),
                                                out_color.data_ptr() if out_color is not None else None,
                                                radii.data_ptr() if radii is not None else None, ptrs, stream), "psb_trainer_backward")
-        if self.world > 1:
-            self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM, group=self.group)
-            if densify_stats:
-                # statistics of the K views of this step: sums for the accumulators, max for the radii
-                self.dist.all_reduce(m.max_radii2D_, op=self.dist.ReduceOp.MAX, group=self.group)
-        _lib.check(self.L.psb_adam_update(m.num_points(), 16, C.byref(cm), ptrs, C.byref(cs), 1.0 / self.world, stream), "psb_adam_update")
+        scale = self.grads.all_reduce(self.group)   # ONE collective per step: 59 floats per Gaussian
+        _lib.check(self.L.psb_adam_update(m.num_points(), 16, C.byref(cm), ptrs, C.byref(cs), scale, stream), "psb_adam_update")
         m.step_ += 1
         self._last = (cam, gt_image, mask, out_color, radii, densify_stats)
+
+    def sync_densify_stats(self):
+        """Reduce the rank-local densification statistics (call right before densify/prune)."""
+        from .parallel import reduce_densify_stats
+        m = self.model
+        reduce_densify_stats(m.max_radii2D_, m.xyz_gradient_accum_, m.denom_, self.group)
 
 
 def fused_loss(image, gt, mask=None, lambda_dssim=0.2, want_grad=True):

@@ -1,0 +1,100 @@
+"""CPU, gloo, world_size 2: the data-parallel step (shard -> per-rank backward -> ONE all-reduce -> Adam) leaves every
+replica with identical parameters, equal to a single process applying the mean gradient of the same views.
+Per-rank compute is the CPU oracle (no GPU here); the reduce / shard / buffer logic is the code the NCCL path uses."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LRS = [0.00032, 0.0025, 0.0025 / 20, 0.05, 0.005, 0.001]
+
+
+def _rank_gradients(rank, P):
+    """Raw-parameter gradients of view `rank` of a tiny shared scene, from the C oracle (+ its activation backward)."""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+    import ctypes as C
+    import oracle_c
+    import photo_slam_b200.synthetic as syn
+    cam0 = syn.make_camera(96, 64, 80.0, 80.0)
+    sc = syn.make_scene(P, cam0, seed=5, scale_px=5.0)
+    R, t = syn.random_pose(np.random.default_rng(10 + rank), 0.1, 0.1)
+    cam = syn.make_camera(96, 64, 80.0, 80.0, R, t)
+    act = syn.activate(sc)
+    f = oracle_c.forward(cam, act)
+    gt = syn.target_image(64, 96, seed=rank)
+    _, _, _, dpix = oracle_c.loss(f["out_color"], gt)
+    b = oracle_c.backward(cam, act, f, dpix)
+    L = oracle_c.lib()
+    g_op, g_sc, g_rot = np.zeros((P, 1), np.float32), np.zeros((P, 3), np.float32), np.zeros((P, 4), np.float32)
+    L.orc_activations_backward(C.c_int(P), oracle_c._p(sc["opacity"]), oracle_c._p(sc["scaling"]), oracle_c._p(sc["rotation"]),
+                               oracle_c._p(b["dL_dopacity"]), oracle_c._p(b["dL_dscale"]), oracle_c._p(b["dL_drot"]), oracle_c._p(g_op),
+                               oracle_c._p(g_sc), oracle_c._p(g_rot))
+    grads = [b["dL_dmean3D"], b["dL_dsh"][:, :1, :], b["dL_dsh"][:, 1:, :], g_op, g_sc, g_rot]
+    params = [sc["xyz"], sc["features_dc"], sc["features_rest"], sc["opacity"], sc["scaling"], sc["rotation"]]
+    return params, grads, oracle_c
+
+
+def _adam_all(params, grads, oracle_c, scale):
+    out = []
+    for p, g, lr in zip(params, grads, LRS):
+        pn, _, _ = oracle_c.adam(p.ravel(), (np.asarray(g, np.float32) * np.float32(scale)).ravel(), np.zeros(p.size, np.float32),
+                                 np.zeros(p.size, np.float32), lr, 1)
+        out.append(pn)
+    return out
+
+
+def _worker(rank, world, port, P, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from photo_slam_b200.parallel import GradBuffer, PER_GAUSSIAN, shard_schedule
+    params, grads, oracle_c = _rank_gradients(rank, P)
+    buf = GradBuffer(P, "cpu")
+    assert buf.flat.numel() == P * PER_GAUSSIAN
+    for v, g in zip(buf.views(), grads):
+        v.copy_(torch.from_numpy(np.ascontiguousarray(g, np.float32)).view_as(v))
+    scale = buf.all_reduce()
+    assert scale == 1.0 / world
+    new = _adam_all(params, [v.numpy() for v in buf.views()], oracle_c, scale)
+    sched = shard_schedule(list(range(11)), rank, world)
+    q.put((rank, [n.copy() for n in new], sched))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_step_matches_single_process_mean_gradient():
+    P, world = 300, 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, P, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        r, new, sched = q.get(timeout=240)
+        res[r] = (new, sched)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # replicas identical
+    for a, b in zip(res[0][0], res[1][0]):
+        assert np.array_equal(a, b)
+    # equal to one process applying the mean gradient of both views
+    params, g0, oracle_c = _rank_gradients(0, P)
+    _, g1, _ = _rank_gradients(1, P)
+    summed = [np.asarray(a, np.float32) + np.asarray(b, np.float32) for a, b in zip(g0, g1)]
+    single = _adam_all(params, summed, oracle_c, 0.5)
+    for a, b in zip(res[0][0], single):
+        assert np.allclose(a, b, rtol=1e-6, atol=1e-9)
+    # schedule sharding: disjoint, interleaved, K consecutive entries per step, remainder dropped
+    assert res[0][1] == [0, 2, 4, 6, 8] and res[1][1] == [1, 3, 5, 7, 9]
