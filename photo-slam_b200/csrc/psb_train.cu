@@ -20,7 +20,7 @@ namespace psb {
 
 namespace {
 
-constexpr int TB = 64;         // Gaussians per block
+constexpr int TB = 128;        // Gaussians per block
 constexpr int REST = 45;       // floats per f_rest row (15 coefficients x 3 channels)
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -62,8 +62,6 @@ __global__ void __launch_bounds__(TB, 5) fused_backward_kernel(int P, TrainTenso
                                                             const uint32_t* __restrict__ counters, uint32_t capacity)
 {
 	__shared__ __align__(128) float s_p[TB * REST];  // f_rest parameter rows of this block (TMA destination)
-	__shared__ __align__(128) float s_m[ADAM ? TB * REST : 4];  // ... their exp_avg rows
-	__shared__ __align__(128) float s_v[ADAM ? TB * REST : 4];  // ... their exp_avg_sq rows
 	__shared__ float s_w[TB][17];                    // SH basis weights per Gaussian (k = 0..15), padded
 	__shared__ float s_g[TB][4];                     // clamp-masked dL/dRGB per Gaussian (0 when not visible)
 	__shared__ __align__(8) uint64_t s_bar;
@@ -83,18 +81,9 @@ __global__ void __launch_bounds__(TB, 5) fused_backward_kernel(int P, TrainTenso
 	if (tid == 0) {
 		mbar_init(&s_bar, 1);
 		mbar_fence_init();
-		// all three 180 B/Gaussian row sets stream in asynchronously while phase 1 computes
-		mbar_arrive_expect_tx(&s_bar, ADAM ? 3 * bulk_bytes : bulk_bytes);
+		mbar_arrive_expect_tx(&s_bar, bulk_bytes);
 		bulk_g2s(s_p, t.p[2] + goff, bulk_bytes, &s_bar);
-		if (ADAM) {
-			bulk_g2s(s_m, t.m[2] + goff, bulk_bytes, &s_bar);
-			bulk_g2s(s_v, t.v[2] + goff, bulk_bytes, &s_bar);
-		}
-		for (int i = 0; i < rem_floats; i++) {  // < 16 trailing bytes (last block)
-			const int o = bulk_bytes / 4 + i;
-			s_p[o] = t.p[2][goff + o];
-			if (ADAM) { s_m[o] = t.m[2][goff + o]; s_v[o] = t.v[2][goff + o]; }
-		}
+		for (int i = 0; i < rem_floats; i++) s_p[bulk_bytes / 4 + i] = t.p[2][goff + bulk_bytes / 4 + i];  // < 16 trailing bytes (last block)
 	}
 	__syncthreads();  // the mbarrier must be initialised before any other thread waits on it
 
@@ -246,27 +235,38 @@ __global__ void __launch_bounds__(TB, 5) fused_backward_kernel(int P, TrainTenso
 		const int k = c / 3 + 1, ch = c - (k - 1) * 3;
 		return s_w[row][k] * s_g[row][ch];
 	};
-#pragma unroll 2
-	for (int i = tid; i < n4; i += TB) {
-		const int e = 4 * i;
-		const float4 g4 = make_float4(grad_of(e), grad_of(e + 1), grad_of(e + 2), grad_of(e + 3));
+	constexpr int PF = 4;  // float4 groups in flight per thread and tensor
+	for (int i0 = tid; i0 < n4; i0 += PF * TB) {
+		float4 m[PF], v[PF];
 		if (ADAM) {
-			float4 p = reinterpret_cast<const float4*>(s_p)[i];
-			float4 m = reinterpret_cast<const float4*>(s_m)[i];
-			float4 v = reinterpret_cast<const float4*>(s_v)[i];
-			adam1(p.x, m.x, v.x, g4.x, lr_rest, ac);
-			adam1(p.y, m.y, v.y, g4.y, lr_rest, ac);
-			adam1(p.z, m.z, v.z, g4.z, lr_rest, ac);
-			adam1(p.w, m.w, v.w, g4.w, lr_rest, ac);
-			gp[i] = p; gm4[i] = m; gv[i] = v;
-		} else {
-			gm4[i] = g4;
+#pragma unroll
+			for (int u = 0; u < PF; u++) {
+				const int i = i0 + u * TB;
+				if (i < n4) { m[u] = gm4[i]; v[u] = gv[i]; }
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < PF; u++) {
+			const int i = i0 + u * TB;
+			if (i >= n4) break;
+			const int e = 4 * i;
+			const float4 g4 = make_float4(grad_of(e), grad_of(e + 1), grad_of(e + 2), grad_of(e + 3));
+			if (ADAM) {
+				float4 p = reinterpret_cast<const float4*>(s_p)[i];
+				adam1(p.x, m[u].x, v[u].x, g4.x, lr_rest, ac);
+				adam1(p.y, m[u].y, v[u].y, g4.y, lr_rest, ac);
+				adam1(p.z, m[u].z, v[u].z, g4.z, lr_rest, ac);
+				adam1(p.w, m[u].w, v[u].w, g4.w, lr_rest, ac);
+				gp[i] = p; gm4[i] = m[u]; gv[i] = v[u];
+			} else {
+				gm4[i] = g4;
+			}
 		}
 	}
 	for (int e = 4 * n4 + tid; e < n_el; e += TB) {  // < 4 trailing elements of the last block
 		const float g = grad_of(e);
 		if (ADAM) {
-			float p = s_p[e], m = s_m[e], v = s_v[e];
+			float p = s_p[e], m = t.m[2][goff + e], v = t.v[2][goff + e];
 			adam1(p, m, v, g, lr_rest, ac);
 			t.p[2][goff + e] = p; t.m[2][goff + e] = m; t.v[2][goff + e] = v;
 		} else {
