@@ -186,6 +186,28 @@ int psb_trainer_stage_times(psb_trainer* t, float* ms, int n);
 int psb_loss(int height, int width, const float* image, const float* gt_image, const float* mask,
              float lambda_dssim, float* dL_dimage, float* out3_host, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Point-cloud helpers exported by the same shared objects in the reference.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Mean squared distance of every point to its 3 nearest neighbours. Replaces SimpleKNN::knn /
+ * distCUDA2 (third_party/simple-knn/simple_knn.h:15-19, spatial.cu:15-26). points [P,3], mean_dists [P], device.
+ * Asynchronous on `stream` (scratch from the stream-ordered allocator; no host round trips). */
+int psb_dist_cuda2(int P, const float* points, float* mean_dists, void* stream);
+
+/* p' = M p for a 4x4 column-major M (rows 0..2 used). Replaces the transform_points kernel behind
+ * transformPoints (src/operate_points.cu:38-50, 73-93). Out-of-place: out_points [P,3]. */
+int psb_transform_points(int P, const float* points, const float* transform, float* out_points, void* stream);
+
+/* For rows with mask != 0: p' = M (scale * p), q' = quaternion(M3x3 * R(q)) (w,x,y,z). Replaces the
+ * scale_and_transform_points kernel behind scaleAndTransformThenMarkVisiblePoints (src/operate_points.cu:52-71,
+ * 95-143). Unmasked rows of the outputs are left untouched. fix_quaternion_write = 0 reproduces the reference's
+ * insert_rot_to_rots exactly (cuda_rasterizer/operate_points.h:170-178 writes z into slot +2 and never writes
+ * slot +3 — SURVEY.md §2.2 quirk 10); != 0 writes the intended (w,x,y,z). */
+int psb_scale_transform_points(int P, float scale, const float* points, const float* rots, const float* transform,
+                               const unsigned char* mask, float* out_points, float* out_rots,
+                               int fix_quaternion_write, void* stream);
+
 /* Standalone sort primitive (tests): stable LSD radix sort of (u32 key, u32 value) pairs on key bits
  * [0, nbits). keys/vals are device arrays of n elements, sorted in place. */
 int psb_debug_sort_pairs(uint32_t* keys, uint32_t* vals, size_t n, int nbits, void* stream);

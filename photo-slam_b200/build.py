@@ -44,5 +44,30 @@ def build(force=False, verbose=False):
     return LIB
 
 
+TORCH_SRC = os.path.join(HERE, "csrc_torch", "rasterize_points.cpp")
+TORCH_LIB = os.path.join(LIBDIR, "libcuda_rasterizer.so")
+
+
+def build_torch_shim(force=False):
+    """libcuda_rasterizer.so: the reference's B1/B2 C++ symbols on top of libpsb200.so (host-only C++/LibTorch)."""
+    build()
+    if not force and os.path.exists(TORCH_LIB) and os.path.getmtime(TORCH_LIB) >= max(os.path.getmtime(TORCH_SRC), os.path.getmtime(LIB)):
+        return TORCH_LIB
+    import torch
+    ti = os.path.dirname(torch.__file__)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+           f"-I{ti}/include", f"-I{ti}/include/torch/csrc/api/include", "-I/usr/local/cuda/include", TORCH_SRC, "-o", TORCH_LIB,
+           f"-L{LIBDIR}", "-lpsb200", f"-L{ti}/lib", "-ltorch", "-ltorch_cpu", "-lc10", "-lc10_cuda", "-ltorch_cuda",
+           "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{ti}/lib"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building libcuda_rasterizer.so")
+    return TORCH_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--torch" in sys.argv:
+        print(build_torch_shim(force="--force" in sys.argv))

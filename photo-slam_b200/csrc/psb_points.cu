@@ -1,0 +1,269 @@
+// Point-cloud helpers that live in the same shared objects as the rasterizer in the reference:
+//   psb_dist_cuda2                  mean squared distance to the 3 nearest neighbours (scale initialisation of new
+//                                   Gaussians) — reference third_party/simple-knn/simple_knn.cu:185-221, spatial.cu:15-26
+//   psb_transform_points            p' = M p                          — reference src/operate_points.cu:38-50, 73-93
+//   psb_scale_transform_points      masked p' = M (s p), q' = quat(M3x3 R(q)) — src/operate_points.cu:52-71,
+//                                   cuda_rasterizer/operate_points.h:55-178
+// simple-knn here: no cudaMalloc / thrust vectors / blocking copies per call (the reference does 7 allocations and 2
+// host round trips): bounds are reduced on the device, scratch comes from the stream-ordered allocator, the Morton
+// sort is the library's own onesweep radix sort.
+#include <cfloat>
+#include "psb_kernels.h"
+#include "../../include/psb200.h"
+
+namespace psb {
+
+namespace {
+
+constexpr int KNN_BOX = 1024;
+
+__device__ __forceinline__ uint32_t f2ord(float f) { const uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float ord2f(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o); }
+
+// bounds[0..2] = min xyz, bounds[3..5] = max xyz as order-preserving uints
+__global__ void knn_bounds_kernel(int P, const float* __restrict__ pts, uint32_t* __restrict__ bounds)
+{
+	float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+#pragma unroll
+		for (int c = 0; c < 3; c++) { const float v = pts[3 * i + c]; mn[c] = fminf(mn[c], v); mx[c] = fmaxf(mx[c], v); }
+	}
+#pragma unroll
+	for (int c = 0; c < 3; c++) {
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) { mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o)); mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o)); }
+	}
+	if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+		for (int c = 0; c < 3; c++) { atomicMin(&bounds[c], f2ord(mn[c])); atomicMax(&bounds[3 + c], f2ord(mx[c])); }
+	}
+}
+
+__device__ __forceinline__ uint32_t prep_morton(uint32_t x)
+{
+	x = (x | (x << 16)) & 0x030000FF;
+	x = (x | (x << 8)) & 0x0300F00F;
+	x = (x | (x << 4)) & 0x030C30C3;
+	x = (x | (x << 2)) & 0x09249249;
+	return x;
+}
+
+__global__ void knn_morton_kernel(int P, const float* __restrict__ pts, const uint32_t* __restrict__ bounds, uint32_t* __restrict__ codes)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P) return;
+	uint32_t code = 0;
+#pragma unroll
+	for (int c = 0; c < 3; c++) {
+		const float mn = ord2f(bounds[c]), mx = ord2f(bounds[3 + c]);
+		const float ext = mx - mn;
+		const float n = ext > 0.f ? (pts[3 * i + c] - mn) / ext : 0.f;
+		code |= prep_morton((uint32_t)(n * 1023.0f)) << c;
+	}
+	codes[i] = code;
+}
+
+struct Box { float mn[3], mx[3]; };
+
+__global__ void __launch_bounds__(KNN_BOX) knn_box_kernel(int P, const float* __restrict__ pts, const uint32_t* __restrict__ order, Box* __restrict__ boxes)
+{
+	__shared__ float s_mn[3][32], s_mx[3][32];
+	const int i = blockIdx.x * KNN_BOX + threadIdx.x;
+	float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+	if (i < P) {
+		const uint32_t g = order[i];
+#pragma unroll
+		for (int c = 0; c < 3; c++) mn[c] = mx[c] = pts[3 * g + c];
+	}
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for (int c = 0; c < 3; c++) {
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) { mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o)); mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o)); }
+		if (lane == 0) { s_mn[c][warp] = mn[c]; s_mx[c][warp] = mx[c]; }
+	}
+	__syncthreads();
+	if (warp == 0) {
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			float a = s_mn[c][lane], b = s_mx[c][lane];
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) { a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o)); b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o)); }
+			if (lane == 0) { boxes[blockIdx.x].mn[c] = a; boxes[blockIdx.x].mx[c] = b; }
+		}
+	}
+}
+
+__device__ __forceinline__ void kbest3(const float3 ref, const float3 p, float* best)
+{
+	const float3 d = make_float3(p.x - ref.x, p.y - ref.y, p.z - ref.z);
+	float dist = d.x * d.x + d.y * d.y + d.z * d.z;
+#pragma unroll
+	for (int j = 0; j < 3; j++) {
+		if (best[j] > dist) { const float t = best[j]; best[j] = dist; dist = t; }
+	}
+}
+__device__ __forceinline__ float box_dist(const Box& b, const float3 p)
+{
+	float3 diff = make_float3(0, 0, 0);
+	if (p.x < b.mn[0] || p.x > b.mx[0]) diff.x = fminf(fabsf(p.x - b.mn[0]), fabsf(p.x - b.mx[0]));
+	if (p.y < b.mn[1] || p.y > b.mx[1]) diff.y = fminf(fabsf(p.y - b.mn[1]), fabsf(p.y - b.mx[1]));
+	if (p.z < b.mn[2] || p.z > b.mx[2]) diff.z = fminf(fabsf(p.z - b.mn[2]), fabsf(p.z - b.mx[2]));
+	return diff.x * diff.x + diff.y * diff.y + diff.z * diff.z;
+}
+
+// exact 3-NN with box pruning (same search as reference simple_knn.cu:147-183)
+__global__ void knn_mean_dist_kernel(int P, const float* __restrict__ pts, const uint32_t* __restrict__ order, const Box* __restrict__ boxes,
+                                     float* __restrict__ dists)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= P) return;
+	auto pt = [&](int k) { const uint32_t g = order[k]; return make_float3(pts[3 * g], pts[3 * g + 1], pts[3 * g + 2]); };
+	const float3 point = pt(idx);
+	float best[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
+	for (int i = max(0, idx - 3); i <= min(P - 1, idx + 3); i++) {
+		if (i == idx) continue;
+		kbest3(point, pt(i), best);
+	}
+	const float reject = best[2];
+	best[0] = best[1] = best[2] = FLT_MAX;
+	const int nbox = (P + KNN_BOX - 1) / KNN_BOX;
+	for (int b = 0; b < nbox; b++) {
+		const float dist = box_dist(boxes[b], point);
+		if (dist > reject || dist > best[2]) continue;
+		const int e = min(P, (b + 1) * KNN_BOX);
+		for (int i = b * KNN_BOX; i < e; i++) {
+			if (i == idx) continue;
+			kbest3(point, pt(i), best);
+		}
+	}
+	dists[order[idx]] = (best[0] + best[1] + best[2]) / 3.0f;
+}
+
+__global__ void transform_points_kernel(int P, const float* __restrict__ pts, const float* __restrict__ m, float* __restrict__ out)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P) return;
+	const float3 p = xform4x3(make_float3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), m);
+	out[3 * i] = p.x; out[3 * i + 1] = p.y; out[3 * i + 2] = p.z;
+}
+
+__global__ void scale_transform_points_kernel(int P, float scale, const float* __restrict__ pts, const float* __restrict__ rots,
+                                              const float* __restrict__ m, const uint8_t* __restrict__ mask, float* __restrict__ out_pts,
+                                              float* __restrict__ out_rots, int fix_quaternion_write)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P || !mask[i]) return;
+	float3 p = make_float3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+	p.x *= scale; p.y *= scale; p.z *= scale;
+	const float3 pt = xform4x3(p, m);
+	out_pts[3 * i] = pt.x; out_pts[3 * i + 1] = pt.y; out_pts[3 * i + 2] = pt.z;
+
+	// rotation of the (w,x,y,z) quaternion by the 3x3 block of m, back to a quaternion (Shoemake 1987)
+	const float qx = rots[4 * i + 1], qy = rots[4 * i + 2], qz = rots[4 * i + 3], qw = rots[4 * i];
+	const float tx = 2.0f * qx, ty = 2.0f * qy, tz = 2.0f * qz;
+	const float twx = tx * qw, twy = ty * qw, twz = tz * qw, txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+	const float R0[3][3] = {{1.0f - (tyy + tzz), txy - twz, txz + twy}, {txy + twz, 1.0f - (txx + tzz), tyz - twx}, {txz - twy, tyz + twx, 1.0f - (txx + tyy)}};
+	float R[3][3];
+#pragma unroll
+	for (int r = 0; r < 3; r++)
+#pragma unroll
+		for (int c = 0; c < 3; c++) R[r][c] = m[r] * R0[0][c] + m[4 + r] * R0[1][c] + m[8 + r] * R0[2][c];
+	float q[4];  // x y z w
+	float t = R[0][0] + R[1][1] + R[2][2];
+	if (t > 0.0f) {
+		t = sqrt(t + 1.0f);
+		q[3] = 0.5f * t;
+		t = 0.5f / t;
+		q[0] = (R[2][1] - R[1][2]) * t; q[1] = (R[0][2] - R[2][0]) * t; q[2] = (R[1][0] - R[0][1]) * t;
+	} else {
+		int a = 0;
+		if (R[1][1] > R[0][0]) a = 1;
+		if (R[2][2] > R[a][a]) a = 2;
+		const int b = (a + 1) % 3, c = (b + 1) % 3;
+		t = sqrt(R[a][a] - R[b][b] - R[c][c] + 1.0f);
+		float xyz[3];
+		xyz[a] = 0.5f * t;
+		t = 0.5f / t;
+		q[3] = (R[c][b] - R[b][c]) * t;
+		xyz[b] = (R[b][a] + R[a][b]) * t;
+		xyz[c] = (R[c][a] + R[a][c]) * t;
+		q[0] = xyz[0]; q[1] = xyz[1]; q[2] = xyz[2];
+	}
+	out_rots[4 * i] = q[3];
+	out_rots[4 * i + 1] = q[0];
+	if (fix_quaternion_write) { out_rots[4 * i + 2] = q[1]; out_rots[4 * i + 3] = q[2]; }
+	else out_rots[4 * i + 2] = q[2];  // the reference writes z into slot +2 and never writes slot +3 (operate_points.h:170-178)
+}
+
+__global__ void init_bounds_kernel(uint32_t* bounds)
+{
+	if (threadIdx.x < 3) bounds[threadIdx.x] = 0xFFFFFFFFu;
+	else if (threadIdx.x < 6) bounds[threadIdx.x] = 0u;
+}
+
+}  // namespace
+
+}  // namespace psb
+
+using namespace psb;
+
+extern "C" {
+
+int psb_dist_cuda2(int P, const float* points, float* mean_dists, void* stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (P < 0 || (P > 0 && (!points || !mean_dists))) { set_error_msg("psb_dist_cuda2: bad argument"); return PSB_ERR_ARG; }
+	if (P == 0) return 0;
+	const SortPlan plan = make_sort_plan(30);
+	const size_t sb = sort_scratch_bytes((size_t)P, plan.npass);
+	const int nbox = (P + KNN_BOX - 1) / KNN_BOX;
+	const size_t bytes = align_up((size_t)P * 4, 256) * 4 + align_up(sb, 256) + align_up((size_t)nbox * sizeof(Box), 256) + 256;
+	char* mem = nullptr;
+	PSB_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&mem), bytes, stream));
+	char* c = mem;
+	uint32_t* keys[2]; uint32_t* vals[2];
+	keys[0] = carve<uint32_t>(c, P, 256); keys[1] = carve<uint32_t>(c, P, 256);
+	vals[0] = carve<uint32_t>(c, P, 256); vals[1] = carve<uint32_t>(c, P, 256);
+	char* scratch = carve<char>(c, sb, 256);
+	Box* boxes = carve<Box>(c, nbox, 256);
+	uint32_t* bounds = carve<uint32_t>(c, 8, 32);
+	init_bounds_kernel<<<1, 32, 0, stream>>>(bounds);
+	int grid = cdiv(P, 256);
+	if (grid > 148 * 8) grid = 148 * 8;
+	knn_bounds_kernel<<<grid, 256, 0, stream>>>(P, points, bounds);
+	knn_morton_kernel<<<cdiv(P, 256), 256, 0, stream>>>(P, points, bounds, keys[0]);
+	PSB_LAUNCH_OK();
+	int rc = radix_sort_pairs(keys, vals, /*iota_vals=*/true, nullptr, (size_t)P, plan, scratch, sb, stream);
+	if (rc == 0) {
+		const uint32_t* order = vals[plan.npass & 1];
+		knn_box_kernel<<<nbox, KNN_BOX, 0, stream>>>(P, points, order, boxes);
+		knn_mean_dist_kernel<<<cdiv(P, 128), 128, 0, stream>>>(P, points, order, boxes, mean_dists);
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) { set_error("knn kernels", e, __FILE__, __LINE__); rc = PSB_ERR_CUDA; }
+	}
+	cudaFreeAsync(mem, stream);
+	return rc;
+}
+
+int psb_transform_points(int P, const float* points, const float* transform, float* out_points, void* stream_)
+{
+	if (P < 0 || (P > 0 && (!points || !transform || !out_points))) { set_error_msg("psb_transform_points: bad argument"); return PSB_ERR_ARG; }
+	if (P == 0) return 0;
+	transform_points_kernel<<<cdiv(P, 256), 256, 0, (cudaStream_t)stream_>>>(P, points, transform, out_points);
+	PSB_LAUNCH_OK();
+	return 0;
+}
+
+int psb_scale_transform_points(int P, float scale, const float* points, const float* rots, const float* transform, const unsigned char* mask,
+                               float* out_points, float* out_rots, int fix_quaternion_write, void* stream_)
+{
+	if (P < 0 || (P > 0 && (!points || !rots || !transform || !mask || !out_points || !out_rots))) { set_error_msg("psb_scale_transform_points: bad argument"); return PSB_ERR_ARG; }
+	if (P == 0) return 0;
+	scale_transform_points_kernel<<<cdiv(P, 256), 256, 0, (cudaStream_t)stream_>>>(P, scale, points, rots, transform, mask, out_points, out_rots,
+	                                                                             fix_quaternion_write);
+	PSB_LAUNCH_OK();
+	return 0;
+}
+
+}  // extern "C"

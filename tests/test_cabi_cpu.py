@@ -62,3 +62,21 @@ def test_rasterizer_frontend_validation_is_host_side():
         r(z(P, 3), z(P, 3), z(P, 1), shs=z(P, 16, 3), scales=z(P, 3), rotations=z(P, 4), cov3D_precomp=z(P, 6))
     with pytest.raises(RuntimeError, match="num_points, 3"):
         rasterizer.RasterizeGaussiansCUDA(z(3), z(P, 2), None, None, None, None, 1.0, None, None, None, 1.0, 1.0, 8, 8, None, 0, None, False)
+
+
+def test_libtorch_shim_exports_the_reference_symbols():
+    """libcuda_rasterizer.so must export the exact Itanium-mangled names that reference include/rasterize_points.h:18-65
+    and cuda_rasterizer/rasterizer.h:24-82 declare (what libgaussian_mapper.so links against). The names below were
+    obtained by compiling a translation unit against the reference's own headers (`nm -u`)."""
+    import os
+    import subprocess
+    lib = os.path.join(os.path.dirname(_lib.LIB_PATH), "libcuda_rasterizer.so")
+    assert os.path.exists(lib), "build it with `python photo-slam_b200/build.py --torch`"
+    out = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True).stdout
+    for sym in ("_Z11markVisibleRN2at6TensorES1_S1_",
+                "_Z22RasterizeGaussiansCUDARKN2at6TensorES2_S2_S2_S2_S2_fS2_S2_S2_ffiiS2_iS2_b",
+                "_Z30RasterizeGaussiansBackwardCUDARKN2at6TensorES2_S2_S2_S2_S2_fS2_S2_S2_ffS2_S2_iS2_S2_iS2_S2_",
+                "_ZN14CudaRasterizer10Rasterizer11markVisibleEiPfS1_S1_Pb",
+                "_ZN14CudaRasterizer10Rasterizer7forwardESt8functionIFPcmEES4_S4_iiiPKfiiS6_S6_S6_S6_S6_fS6_S6_S6_S6_S6_ffbPfPi",
+                "_ZN14CudaRasterizer10Rasterizer8backwardEiiiiPKfiiS2_S2_S2_S2_fS2_S2_S2_S2_S2_ffPKiPcS5_S5_S2_PfS6_S6_S6_S6_S6_S6_S6_S6_"):
+        assert sym in out, sym

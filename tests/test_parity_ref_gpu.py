@@ -267,3 +267,38 @@ def test_autograd_wrapper_matches_reference_chain(cuda):
         rasterizer.GaussianRasterizer(rs)(leaves["means3D"], means2D, leaves["opacities"], shs=leaves["shs"],
                                           colors_precomp=torch.rand((P, 3), device=cuda), scales=leaves["scales"],
                                           rotations=leaves["rotations"])
+
+
+def test_libtorch_shim_same_results_as_cabi(cuda):
+    """The C++/LibTorch drop-in (libcuda_rasterizer.so: RasterizeGaussiansCUDA / BackwardCUDA / markVisible and
+    CudaRasterizer::Rasterizer::forward with std::function allocators) returns exactly what the C-ABI returns."""
+    import os
+    from photo_slam_b200 import _lib
+    rasterizer, ref_gpu = _mods()
+    shim = os.path.join(os.path.dirname(_lib.LIB_PATH), "libcuda_rasterizer.so")
+    if not os.path.exists(shim):
+        pytest.skip("libcuda_rasterizer.so not built")
+    torch.ops.load_library(shim)
+    P, D = 40_000, 3
+    cam, sc, act, g, c = scene_tensors(P, "euroc", seed=8, pose_seed=12, dev=cuda)
+    bg = torch.tensor((0.2, 0.1, 0.0), device=cuda)
+    e = torch.empty(0, device=cuda)
+    args = (bg, g["means3D"], e, g["opacities"], g["scales"], g["rotations"], 1.0, e, c["viewmatrix"], c["projmatrix"], c["tanfovx"],
+            c["tanfovy"], c["H"], c["W"], g["shs"], D, c["campos"], False)
+    a = rasterizer.RasterizeGaussiansCUDA(*args)
+    b = torch.ops.psb200.rasterize_gaussians(*args)
+    assert a[0] == b[0] and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    dL = torch.randn_like(a[1])
+    bargs = lambda o: (bg, g["means3D"], o[2], e, g["scales"], g["rotations"], 1.0, e, c["viewmatrix"], c["projmatrix"], c["tanfovx"],
+                       c["tanfovy"], dL, g["shs"], D, c["campos"], o[3], o[0], o[4], o[5])
+    ga = rasterizer.RasterizeGaussiansBackwardCUDA(*bargs(a))
+    gb = torch.ops.psb200.rasterize_gaussians_backward(*bargs(b))
+    for x, y in zip(ga, gb):
+        assert ((x - y).double().norm() / (y.double().norm() + 1e-30)).item() < 1e-5
+    assert torch.equal(torch.ops.psb200.mark_visible(g["means3D"], c["viewmatrix"], c["projmatrix"]),
+                       rasterizer.markVisible(g["means3D"], c["viewmatrix"], c["projmatrix"]))
+    R2, out2, rad2 = torch.ops.psb200.b2_forward(bg, g["means3D"], g["opacities"], g["scales"], g["rotations"], c["viewmatrix"], c["projmatrix"],
+                                                c["tanfovx"], c["tanfovy"], c["H"], c["W"], g["shs"], D, c["campos"])
+    assert R2 == a[0] and torch.equal(out2, a[1]) and torch.equal(rad2, a[2])
+    with pytest.raises(RuntimeError):
+        torch.ops.psb200.rasterize_gaussians(bg, torch.zeros((4, 2), device=cuda), e, e, e, e, 1.0, e, e, e, 1.0, 1.0, 8, 8, e, 0, e, False)
