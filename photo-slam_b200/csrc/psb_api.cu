@@ -159,6 +159,7 @@ int psb_rasterize_backward(int P, int D, int M, int R, const float* background, 
 	sink.conic = dL_dconic; sink.conic_stride = 4;
 	sink.opacity = dL_dopacity; sink.opacity_stride = 1;
 	sink.color = dL_dcolor; sink.color_stride = 3;
+	sink.packed = 0;
 	int rc;
 	if (R > 0)
 		if ((rc = launch_render_backward(cam, img.ranges, bin.inst[res], geom.rec, background, img.final_T, img.n_contrib, dL_dpix, sink, stream))) return rc;

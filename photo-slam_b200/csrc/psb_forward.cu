@@ -170,25 +170,38 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(int P, const
 		if (i < warp) wb += s_warp[i];
 		block_total += s_warp[i];
 	}
-	if (tid == 0) {
+	if (warp == 0) {
+		// warp-wide decoupled look-back: 32 predecessors per round trip
 		uint32_t excl = 0;
 		volatile uint32_t* st = status;
 		if (tile == 0) {
-			st[0] = (2u << 30) | block_total;
+			if (lane == 0) st[0] = (2u << 30) | block_total;
 		} else {
-			st[tile] = (1u << 30) | block_total;
+			if (lane == 0) st[tile] = (1u << 30) | block_total;
 			int p = (int)tile - 1;
 			while (true) {
-				uint32_t s;
-				do { s = st[p]; } while ((s >> 30) == 0u);
-				excl += s & ((1u << 30) - 1u);
-				if ((s >> 30) == 2u) break;
-				p--;
+				const int q = p - lane;
+				uint32_t s = (q >= 0) ? st[q] : (2u << 30);
+				// lanes closer to the tile must be published before a farther inclusive value can be used
+				uint32_t unpublished = __ballot_sync(0xffffffffu, (s >> 30) == 0u);
+				uint32_t incl = __ballot_sync(0xffffffffu, (s >> 30) == 2u);
+				const int first_incl = incl ? (__ffs(incl) - 1) : 32;
+				const int first_unpub = unpublished ? (__ffs(unpublished) - 1) : 32;
+				if (first_unpub < first_incl) continue;  // poll again (same window)
+				const int upto = min(first_incl, 31);
+				uint32_t contrib = (lane <= upto) ? (s & ((1u << 30) - 1u)) : 0u;
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+				excl += contrib;
+				if (first_incl < 32) break;
+				p -= 32;
 			}
-			st[tile] = (2u << 30) | ((excl + block_total) & ((1u << 30) - 1u));
+			if (lane == 0) st[tile] = (2u << 30) | ((excl + block_total) & ((1u << 30) - 1u));
 		}
-		s_prefix = excl;
-		if ((int)(tile + 1) * SCAN_TILE >= P) counters[0] = excl + block_total;
+		if (lane == 0) {
+			s_prefix = excl;
+			if ((int)(tile + 1) * SCAN_TILE >= P) counters[0] = excl + block_total;
+		}
 	}
 	__syncthreads();
 	uint32_t run = s_prefix + wb + inc - sum;

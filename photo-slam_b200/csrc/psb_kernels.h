@@ -29,6 +29,7 @@ struct GradSink {
 	float* conic;   int conic_stride;    // .x .y .w at +0 +1 +3
 	float* opacity; int opacity_stride;
 	float* color;   int color_stride;    // rgb at +0..2
+	int packed;                          // != 0: one 16-byte aligned [P][12] row layout (mean2D base), vector reductions
 };
 
 // Outputs of the per-Gaussian backward (any pointer may be null = not wanted).

@@ -427,15 +427,23 @@ __global__ void __launch_bounds__(RB) render_bwd_kernel(const uint2* __restrict_
 					}
 				}
 				const uint32_t g = sm.gid[st][tid];
-				atomicAdd(sink.mean2D + (size_t)g * sink.mean2D_stride + 0, a[0]);
-				atomicAdd(sink.mean2D + (size_t)g * sink.mean2D_stride + 1, a[1]);
-				atomicAdd(sink.conic + (size_t)g * sink.conic_stride + 0, a[2]);
-				atomicAdd(sink.conic + (size_t)g * sink.conic_stride + 1, a[3]);
-				atomicAdd(sink.conic + (size_t)g * sink.conic_stride + 3, a[4]);
-				atomicAdd(sink.opacity + (size_t)g * sink.opacity_stride, a[5]);
-				atomicAdd(sink.color + (size_t)g * sink.color_stride + 0, a[6]);
-				atomicAdd(sink.color + (size_t)g * sink.color_stride + 1, a[7]);
-				atomicAdd(sink.color + (size_t)g * sink.color_stride + 2, a[8]);
+				if (sink.packed) {
+					// trainer path: the 9 sums of a Gaussian live in one 48-byte row -> three 128-bit vector reductions
+					float4* row = reinterpret_cast<float4*>(sink.mean2D + (size_t)g * 12);
+					atomicAdd(row + 0, make_float4(a[0], a[1], 0.f, a[2]));
+					atomicAdd(row + 1, make_float4(a[3], 0.f, a[4], a[5]));
+					atomicAdd(row + 2, make_float4(a[6], a[7], a[8], 0.f));
+				} else {
+					atomicAdd(sink.mean2D + (size_t)g * sink.mean2D_stride + 0, a[0]);
+					atomicAdd(sink.mean2D + (size_t)g * sink.mean2D_stride + 1, a[1]);
+					atomicAdd(sink.conic + (size_t)g * sink.conic_stride + 0, a[2]);
+					atomicAdd(sink.conic + (size_t)g * sink.conic_stride + 1, a[3]);
+					atomicAdd(sink.conic + (size_t)g * sink.conic_stride + 3, a[4]);
+					atomicAdd(sink.opacity + (size_t)g * sink.opacity_stride, a[5]);
+					atomicAdd(sink.color + (size_t)g * sink.color_stride + 0, a[6]);
+					atomicAdd(sink.color + (size_t)g * sink.color_stride + 1, a[7]);
+					atomicAdd(sink.color + (size_t)g * sink.color_stride + 2, a[8]);
+				}
 			}
 		}
 	}

@@ -155,14 +155,25 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint32_t*
 			st_volatile(st, ST_FLAG_INC | count);
 		} else {
 			st_volatile(st, ST_FLAG_AGG | count);
+			// Decoupled look-back. Tiles of one wave start together, so the inclusive prefix of the nearest
+			// predecessors is usually not published yet and the walk has to add up to a few hundred aggregates:
+			// read LB predecessors per round trip (independent loads) instead of one.
+			constexpr int LB = 8;
 			int p = (int)tile - 1;
-			while (true) {
-				uint32_t s;
-				const uint32_t* sp = status + (size_t)p * RS_RADIX + tid;
-				do { s = ld_volatile(sp); } while ((s >> 30) == 0u);
-				excl_prev += s & ST_VAL_MASK;
-				if ((s >> 30) == 2u) break;
-				p--;
+			bool found = false;
+			while (!found) {
+				uint32_t sv[LB];
+#pragma unroll
+				for (int u = 0; u < LB; u++) sv[u] = (p - u >= 0) ? ld_volatile(status + (size_t)(p - u) * RS_RADIX + tid) : ST_FLAG_INC;
+#pragma unroll
+				for (int u = 0; u < LB; u++) {
+					if (found) break;
+					uint32_t s = sv[u];
+					while ((s >> 30) == 0u) s = ld_volatile(status + (size_t)(p - u) * RS_RADIX + tid);  // not published yet: poll this one
+					excl_prev += s & ST_VAL_MASK;
+					if ((s >> 30) == 2u) found = true;
+				}
+				p -= LB;
 			}
 			st_volatile(st, ST_FLAG_INC | ((excl_prev + count) & ST_VAL_MASK));
 		}

@@ -180,6 +180,7 @@ int step_impl(psb_trainer* t, int P, int M, const psb_model* model, const psb_ca
 	sink.conic = t->sink + 3; sink.conic_stride = 12;
 	sink.opacity = t->sink + 7; sink.opacity_stride = 12;
 	sink.color = t->sink + 8; sink.color_stride = 12;
+	sink.packed = 1;
 	const int res = make_sort_plan(tile_id_bits(cam.grid_x * cam.grid_y)).npass & 1;
 	if ((rc = launch_render_backward(cam, img.ranges, bin.inst[res], geom.rec, background, img.final_T, img.n_contrib, t->dL_dpix, sink, stream))) return rc;
 	t->mark(6, stream);
