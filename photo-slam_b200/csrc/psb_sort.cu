@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) rs_scan_hist_kernel(uint32_t* __restrict_
 }
 
 template <bool IOTA>
-__global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+__global__ void __launch_bounds__(RS_THREADS, 3) rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                                 uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                                 const uint32_t* __restrict__ n_dev, uint32_t n_host, int shift, int bits,
                                                                 const uint32_t* __restrict__ hist_excl, uint32_t* __restrict__ ticket,
@@ -122,22 +122,35 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const uint32_t*
 		else val[i] = ok ? vals_in[idx] : 0u;
 	}
 
-	// 2. stable rank inside the warp chunk
+	// 2. stable rank inside the warp chunk. Lanes holding the same digit are found with one ballot per digit bit
+	//    (independent across the 16 items, unlike MATCH.ANY whose long latency serialises the loop); the lowest
+	//    such lane reserves the run in the warp's counter row with ONE shared-memory atomic (same-address atomics
+	//    of a warp retire in program order, which keeps the ranking stable across the 16 rounds).
 	const uint32_t lanemask_lt = (1u << lane) - 1u;
+	constexpr int RG = 8;  // items ranked per group (bounds the live registers, still 8-way ILP)
 #pragma unroll
-	for (int i = 0; i < RS_ITEMS; i++) {
-		const uint32_t d = (key[i] >> shift) & mask;
-		const uint32_t peers = __match_any_sync(0xffffffffu, d);
-		const uint32_t below = __popc(peers & lanemask_lt);
-		const int leader = __ffs(peers) - 1;
-		uint32_t pre = 0;
-		if (lane == leader) {
-			pre = s_warp_hist[warp][d];
-			s_warp_hist[warp][d] = pre + __popc(peers);
+	for (int g0 = 0; g0 < RS_ITEMS; g0 += RG) {
+		uint32_t pre[RG];
+#pragma unroll
+		for (int u = 0; u < RG; u++) {
+			const int i = g0 + u;
+			const uint32_t d = (key[i] >> shift) & mask;
+			uint32_t peers = 0xffffffffu;
+			for (int bit = 0; bit < bits; bit++) {
+				const bool one = (d >> bit) & 1u;
+				const uint32_t bal = __ballot_sync(0xffffffffu, one);
+				peers &= one ? bal : ~bal;
+			}
+			const int leader = __ffs(peers) - 1;
+			rank[i] = (uint32_t)__popc(peers & lanemask_lt) | ((uint32_t)leader << 8);
+			pre[u] = 0;
+			if (lane == leader) pre[u] = atomicAdd(&s_warp_hist[warp][d], (uint32_t)__popc(peers));
 		}
-		pre = __shfl_sync(0xffffffffu, pre, leader);
-		rank[i] = pre + below;
-		__syncwarp();
+#pragma unroll
+		for (int u = 0; u < RG; u++) {
+			const int i = g0 + u;
+			rank[i] = (rank[i] & 0xffu) + __shfl_sync(0xffffffffu, pre[u], (int)(rank[i] >> 8));
+		}
 	}
 	__syncthreads();
 
