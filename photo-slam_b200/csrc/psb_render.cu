@@ -16,6 +16,7 @@
 //
 // Blending semantics (thresholds, order of operations, n_contrib bookkeeping) follow reference
 // cuda_rasterizer/forward.cu:261-374 and backward.cu:399-557.
+#include <cstdlib>
 #include "psb_common.cuh"
 #include "psb_kernels.h"
 
@@ -54,23 +55,8 @@ __device__ __forceinline__ bool splat_reaches_tile(const float4 q0, const float4
 	return !(qmin > thr + pad);
 }
 
-// Stage one batch: entry i of the batch <- record of Gaussian list[pos(i)].
-template <bool REVERSE>
-__device__ __forceinline__ void stage_batch(GaussRec* s_rec, uint32_t* s_gid, uint64_t* bar, const GaussRec* __restrict__ rec,
-                                            const uint32_t* __restrict__ point_list, uint32_t list_begin, int n, int batch, int tid)
-{
-	const int e = batch * RB + tid;  // entry number in traversal order
-	const int cnt = min(RB, n - batch * RB);
-	if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)cnt * (uint32_t)sizeof(GaussRec));
-	if (e < n) {
-		const uint32_t pos = REVERSE ? (list_begin + (uint32_t)(n - 1 - e)) : (list_begin + (uint32_t)e);
-		const uint32_t g = point_list[pos];
-		s_gid[tid] = g;
-		bulk_g2s(&s_rec[tid], &rec[g], (uint32_t)sizeof(GaussRec), bar);
-	}
-}
-
-// Ordered compaction of `keep` flags over the block; returns total, writes kept thread ids to s_cidx.
+// Ordered compaction of `keep` flags over the block; returns total, writes kept entry ids to s_cidx.
+template <int NWARPS>
 __device__ __forceinline__ int compact_block(bool keep, uint8_t* s_cidx, int* s_wcnt, int tid)
 {
 	const int lane = tid & 31, warp = tid >> 5;
@@ -79,7 +65,7 @@ __device__ __forceinline__ int compact_block(bool keep, uint8_t* s_cidx, int* s_
 	__syncthreads();
 	int base = 0, total = 0;
 #pragma unroll
-	for (int w = 0; w < RB / 32; w++) {
+	for (int w = 0; w < NWARPS; w++) {
 		const int c = s_wcnt[w];
 		if (w < warp) base += c;
 		total += c;
@@ -91,65 +77,97 @@ __device__ __forceinline__ int compact_block(bool keep, uint8_t* s_cidx, int* s_
 
 }  // namespace
 
+// Thread/pixel geometry shared by both tile kernels: PPT pixels per thread, 256 / PPT threads per 16x16 tile.
+// A warp owns an 8-wide, 4*PPT-tall footprint; lane (lx, ly) = (lane & 7, lane >> 3) owns the pixels of rows
+// ly, ly + 4, ... ly + 4 (PPT - 1) of that footprint (same column: dx is shared by a thread's pixels).
+template <int PPT>
+struct TileGeom {
+	static constexpr int THREADS = PSB_TILE_PIX / PPT;
+	static constexpr int NWARPS = THREADS / 32;
+	static constexpr int FOOT_H = 4 * PPT;
+	static constexpr int WARPS_Y = PSB_TILE_Y / FOOT_H;
+};
+
 // =================================================================================================
 // Forward
 // =================================================================================================
-__global__ void __launch_bounds__(RB) render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                                                        const GaussRec* __restrict__ rec, int W, int H, const float* __restrict__ bg_color,
-                                                        float* __restrict__ out_color, float* __restrict__ final_T,
-                                                        uint32_t* __restrict__ n_contrib)
+template <int PPT>
+__global__ void __launch_bounds__(TileGeom<PPT>::THREADS) render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                                                                            const GaussRec* __restrict__ rec, int W, int H,
+                                                                            const float* __restrict__ bg_color, float* __restrict__ out_color,
+                                                                            float* __restrict__ final_T, uint32_t* __restrict__ n_contrib)
 {
-	__shared__ __align__(16) GaussRec s_rec[2][RB];
-	__shared__ uint32_t s_gid[2][RB];
-	__shared__ uint8_t s_cidx[RB];
-	__shared__ int s_wcnt[RB / 32];
+	using G = TileGeom<PPT>;
+	constexpr int NT = G::THREADS;  // = list entries staged per batch (one per thread)
+	__shared__ __align__(16) GaussRec s_rec[2][NT];
+	__shared__ uint8_t s_cidx[NT];
+	__shared__ int s_wcnt[G::NWARPS];
 	__shared__ __align__(8) uint64_t s_bar[2];
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int tile_x0 = blockIdx.x * PSB_TILE_X, tile_y0 = blockIdx.y * PSB_TILE_Y;
-	const int px = tile_x0 + (warp & 1) * 8 + (lane & 7);
-	const int py = tile_y0 + (warp >> 1) * 4 + (lane >> 3);
-	const bool inside = px < W && py < H;
-	const uint32_t pix_id = (uint32_t)W * py + px;
-	const float2 pixf = make_float2((float)px, (float)py);
+	const int wx = tile_x0 + (warp % 2) * 8, wy = tile_y0 + (warp / 2) * G::FOOT_H;
+	const int px = wx + (lane & 7);
+	const float pixfx = (float)px;
+	int py[PPT];
+	float pixfy[PPT];
+	bool done[PPT];
+	float T[PPT], C[PPT][3];
+	uint32_t last_contributor[PPT];
+#pragma unroll
+	for (int p = 0; p < PPT; p++) {
+		py[p] = wy + (lane >> 3) + 4 * p;
+		pixfy[p] = (float)py[p];
+		done[p] = !(px < W && py[p] < H);
+		T[p] = 1.0f;
+		C[p][0] = C[p][1] = C[p][2] = 0.f;
+		last_contributor[p] = 0;
+	}
 	const float rx0 = (float)tile_x0, ry0 = (float)tile_y0;
 	const float rx1 = (float)(min(tile_x0 + PSB_TILE_X, W) - 1), ry1 = (float)(min(tile_y0 + PSB_TILE_Y, H) - 1);
-	// pixel rectangle of this warp's 8x4 footprint (clamped to the image; degenerate if the warp is outside)
-	const float wx0 = (float)(tile_x0 + (warp & 1) * 8), wy0 = (float)(tile_y0 + (warp >> 1) * 4);
-	const float wx1 = fmaxf(wx0, fminf(wx0 + 7.f, (float)(W - 1))), wy1 = fmaxf(wy0, fminf(wy0 + 3.f, (float)(H - 1)));
+	// pixel rectangle of this warp's footprint (clamped to the image; degenerate if the warp is outside)
+	const float wx0 = (float)wx, wy0 = (float)wy;
+	const float wx1 = fmaxf(wx0, fminf(wx0 + 7.f, (float)(W - 1))), wy1 = fmaxf(wy0, fminf(wy0 + (float)(G::FOOT_H - 1), (float)(H - 1)));
 
 	const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
 	const int n = (int)(range.y - range.x);
-	const int nbatch = (n + RB - 1) / RB;
+	const int nbatch = (n + NT - 1) / NT;
+
+	auto stage = [&](int batch, int st) {
+		const int e = batch * NT + tid;
+		if (tid == 0) mbar_arrive_expect_tx(&s_bar[st], (uint32_t)min(NT, n - batch * NT) * (uint32_t)sizeof(GaussRec));
+		if (e < n) bulk_g2s(&s_rec[st][tid], &rec[point_list[range.x + (uint32_t)e]], (uint32_t)sizeof(GaussRec), &s_bar[st]);
+	};
+	auto all_done = [&]() {
+		bool d = true;
+#pragma unroll
+		for (int p = 0; p < PPT; p++) d = d && done[p];
+		return d;
+	};
 
 	if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
 	__syncthreads();
-	if (nbatch > 0) stage_batch<false>(s_rec[0], s_gid[0], &s_bar[0], rec, point_list, range.x, n, 0, tid);
-
-	bool done = !inside;
-	float T = 1.0f;
-	uint32_t last_contributor = 0;
-	float C[3] = {0.f, 0.f, 0.f};
+	if (nbatch > 0) stage(0, 0);
 
 	for (int b = 0; b < nbatch; b++) {
 		const int st = b & 1;
 		// (the barrier also orders stage reuse: every thread has left batch b-1)
-		if (__syncthreads_count(done) == RB) {
+		if (__syncthreads_count(all_done()) == NT) {
 			mbar_wait(&s_bar[st], (uint32_t)((b >> 1) & 1));  // drain the in-flight copy of batch b before exiting
 			break;
 		}
-		if (b + 1 < nbatch) stage_batch<false>(s_rec[st ^ 1], s_gid[st ^ 1], &s_bar[st ^ 1], rec, point_list, range.x, n, b + 1, tid);
+		if (b + 1 < nbatch) stage(b + 1, st ^ 1);
 		mbar_wait(&s_bar[st], (uint32_t)((b >> 1) & 1));
 
-		const int cnt = min(RB, n - b * RB);
+		const int cnt = min(NT, n - b * NT);
 		bool keep = false;
 		if (tid < cnt) keep = splat_reaches_tile(s_rec[st][tid].q0, s_rec[st][tid].q1, rx0, ry0, rx1, ry1);
-		const int ccount = compact_block(keep, s_cidx, s_wcnt, tid);
+		const int ccount = compact_block<G::NWARPS>(keep, s_cidx, s_wcnt, tid);
 
-		// Second, per-warp cull: each lane tests one surviving entry against this warp's 8x4 pixel footprint
+		// Second, per-warp cull: each lane tests one surviving entry against this warp's pixel footprint
 		// (32 entries per ballot), then the warp walks only the entries that can reach one of its pixels.
 		for (int c0 = 0; c0 < ccount; c0 += 32) {
-			if (__all_sync(0xffffffffu, done)) break;
+			if (__all_sync(0xffffffffu, all_done())) break;
 			const int kk = c0 + lane;
 			int j = 0;
 			bool hit = false;
@@ -162,35 +180,43 @@ __global__ void __launch_bounds__(RB) render_fwd_kernel(const uint2* __restrict_
 				const int src = __ffs(hits) - 1;
 				hits &= hits - 1;
 				const int jj = __shfl_sync(0xffffffffu, j, src);
-				if (done) continue;
 				const float4 q0 = s_rec[st][jj].q0;
 				const float4 q1 = s_rec[st][jj].q1;
 				const float2 xy = make_float2(q0.x, q0.y);
-				const float2 d = make_float2(xy.x - pixf.x, xy.y - pixf.y);
 				const float4 con_o = make_float4(q0.z, q0.w, q1.x, q1.y);
-				const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-				if (power > 0.0f) continue;
-				if (power < q1.z) continue;  // below pmin: alpha < 1/255 for certain, skip exp (see GaussRec)
-				const float alpha = min(0.99f, con_o.w * exp(power));
-				if (alpha < 1.0f / 255.0f) continue;
-				const float test_T = T * (1 - alpha);
-				if (test_T < 0.0001f) { done = true; continue; }
-				const float4 q2 = s_rec[st][jj].q2;
-				C[0] += q2.x * alpha * T;
-				C[1] += q2.y * alpha * T;
-				C[2] += q2.z * alpha * T;
-				T = test_T;
-				last_contributor = (uint32_t)(b * RB + jj + 1);
+				const uint32_t contributor = (uint32_t)(b * NT + jj + 1);
+#pragma unroll
+				for (int p = 0; p < PPT; p++) {
+					if (done[p]) continue;
+					const float2 d = make_float2(xy.x - pixfx, xy.y - pixfy[p]);
+					const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+					if (power > 0.0f) continue;
+					if (power < q1.z) continue;  // below pmin: alpha < 1/255 for certain, skip exp (see GaussRec)
+					const float alpha = min(0.99f, con_o.w * exp(power));
+					if (alpha < 1.0f / 255.0f) continue;
+					const float test_T = T[p] * (1 - alpha);
+					if (test_T < 0.0001f) { done[p] = true; continue; }
+					const float4 q2 = s_rec[st][jj].q2;
+					C[p][0] += q2.x * alpha * T[p];
+					C[p][1] += q2.y * alpha * T[p];
+					C[p][2] += q2.z * alpha * T[p];
+					T[p] = test_T;
+					last_contributor[p] = contributor;
+				}
 			}
 		}
 	}
 
-	if (inside) {
-		final_T[pix_id] = T;
-		n_contrib[pix_id] = last_contributor;
-		const size_t HW = (size_t)H * W;
+	const size_t HW = (size_t)H * W;
 #pragma unroll
-		for (int ch = 0; ch < 3; ch++) out_color[ch * HW + pix_id] = C[ch] + T * bg_color[ch];
+	for (int p = 0; p < PPT; p++) {
+		if (px < W && py[p] < H) {
+			const uint32_t pix_id = (uint32_t)W * py[p] + px;
+			final_T[pix_id] = T[p];
+			n_contrib[pix_id] = last_contributor[p];
+#pragma unroll
+			for (int ch = 0; ch < 3; ch++) out_color[ch * HW + pix_id] = C[p][ch] + T[p] * bg_color[ch];
+		}
 	}
 }
 
@@ -243,56 +269,79 @@ __device__ __forceinline__ float warp_reduce9(const float v[9], int lane)
 	return dsum;
 }
 
-// Backward batch geometry: 128 list entries per batch (staged by the first 128 threads), 256 pixel threads.
-constexpr int RBB = 128;
-constexpr int ACC_ROW = 73;  // floats per entry: 8 warps x 9 sums (+1 pad: conflict-free row reads)
+// Backward batch geometry: RBB list entries per batch, staged by the first RBB threads.
+template <int PPT>
 struct BwdSmem {
+	static constexpr int RBB = TileGeom<PPT>::THREADS < 128 ? TileGeom<PPT>::THREADS : 128;
+	static constexpr int ACC_ROW = TileGeom<PPT>::NWARPS * 9 + 1;  // floats per entry: NWARPS x 9 sums (+1 pad: conflict-free row reads)
 	GaussRec rec[2][RBB];
 	float acc[RBB * ACC_ROW];
 	unsigned long long dirty[RBB];  // byte w != 0: warp w wrote its 9 sums for this entry
 	uint32_t gid[2][RBB];
 	uint64_t bar[2];
-	int wcnt[RB / 32];
+	int wcnt[TileGeom<PPT>::NWARPS];
 	uint8_t cidx[RBB];
 };
 
-__global__ void __launch_bounds__(RB) render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                                                        const GaussRec* __restrict__ rec, int W, int H, const float* __restrict__ bg_color,
-                                                        const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
-                                                        const float* __restrict__ dL_dpixels, GradSink sink)
+template <int PPT>
+__global__ void __launch_bounds__(TileGeom<PPT>::THREADS) render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                                                                            const GaussRec* __restrict__ rec, int W, int H,
+                                                                            const float* __restrict__ bg_color, const float* __restrict__ final_Ts,
+                                                                            const uint32_t* __restrict__ n_contrib,
+                                                                            const float* __restrict__ dL_dpixels, GradSink sink)
 {
+	using G = TileGeom<PPT>;
+	using SM = BwdSmem<PPT>;
+	constexpr int NT = G::THREADS, RBB = SM::RBB, ACC_ROW = SM::ACC_ROW;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+	SM& sm = *reinterpret_cast<SM*>(smem_raw);
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int tile_x0 = blockIdx.x * PSB_TILE_X, tile_y0 = blockIdx.y * PSB_TILE_Y;
-	const int px = tile_x0 + (warp & 1) * 8 + (lane & 7);
-	const int py = tile_y0 + (warp >> 1) * 4 + (lane >> 3);
-	const bool inside = px < W && py < H;
-	const uint32_t pix_id = (uint32_t)W * py + px;
-	const float2 pixf = make_float2((float)px, (float)py);
+	const int wx = tile_x0 + (warp % 2) * 8, wy = tile_y0 + (warp / 2) * G::FOOT_H;
+	const int px = wx + (lane & 7);
+	const float pixfx = (float)px;
 	const float rx0 = (float)tile_x0, ry0 = (float)tile_y0;
 	const float rx1 = (float)(min(tile_x0 + PSB_TILE_X, W) - 1), ry1 = (float)(min(tile_y0 + PSB_TILE_Y, H) - 1);
-	// pixel rectangle of this warp's 8x4 footprint (clamped to the image; degenerate if the warp is outside)
-	const float wx0 = (float)(tile_x0 + (warp & 1) * 8), wy0 = (float)(tile_y0 + (warp >> 1) * 4);
-	const float wx1 = fmaxf(wx0, fminf(wx0 + 7.f, (float)(W - 1))), wy1 = fmaxf(wy0, fminf(wy0 + 3.f, (float)(H - 1)));
+	const float wx0 = (float)wx, wy0 = (float)wy;
+	const float wx1 = fmaxf(wx0, fminf(wx0 + 7.f, (float)(W - 1))), wy1 = fmaxf(wy0, fminf(wy0 + (float)(G::FOOT_H - 1), (float)(H - 1)));
+	const size_t HW = (size_t)H * W;
 
 	const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
 
-	const float T_final = inside ? final_Ts[pix_id] : 0;
-	float T = T_final;
-	const int last_contributor = inside ? (int)n_contrib[pix_id] : 0;
+	float pixfy[PPT], T_final[PPT], T[PPT], accum_rec[PPT][3], dL_dpixel[PPT][3], last_alpha[PPT], last_color[PPT][3], bg_dot_dpixel[PPT];
+	int last_contributor[PPT];
+	int my_max = 0;
+#pragma unroll
+	for (int p = 0; p < PPT; p++) {
+		const int py = wy + (lane >> 3) + 4 * p;
+		const bool inside = px < W && py < H;
+		const uint32_t pix_id = (uint32_t)W * py + px;
+		pixfy[p] = (float)py;
+		T_final[p] = inside ? final_Ts[pix_id] : 0;
+		T[p] = T_final[p];
+		last_contributor[p] = inside ? (int)n_contrib[pix_id] : 0;
+		my_max = max(my_max, last_contributor[p]);
+		last_alpha[p] = 0;
+		bg_dot_dpixel[p] = 0;
+#pragma unroll
+		for (int i = 0; i < 3; i++) {
+			accum_rec[p][i] = 0.f;
+			last_color[p][i] = 0.f;
+			dL_dpixel[p][i] = inside ? dL_dpixels[i * HW + pix_id] : 0.f;
+			bg_dot_dpixel[p] += bg_color[i] * dL_dpixel[p][i];
+		}
+	}
 
 	// Nothing behind the deepest last contributor of the tile can receive gradient: start there.
-	int maxc = __reduce_max_sync(0xffffffffu, last_contributor);
-	const int warp_maxc = maxc;
-	if (lane == 0) sm.wcnt[warp] = maxc;
+	const int warp_maxc = __reduce_max_sync(0xffffffffu, my_max);
+	if (lane == 0) sm.wcnt[warp] = warp_maxc;
 	if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); mbar_fence_init(); }
 	if (tid < RBB) sm.dirty[tid] = 0ull;
 	__syncthreads();
-	maxc = 0;
+	int maxc = 0;
 #pragma unroll
-	for (int w = 0; w < RB / 32; w++) maxc = max(maxc, sm.wcnt[w]);
+	for (int w = 0; w < G::NWARPS; w++) maxc = max(maxc, sm.wcnt[w]);
 	__syncthreads();
 	const int n = min(maxc, (int)(range.y - range.x));
 	if (n == 0) return;
@@ -309,20 +358,8 @@ __global__ void __launch_bounds__(RB) render_bwd_kernel(const uint2* __restrict_
 	};
 	stage(0, 0);
 
-	float accum_rec[3] = {0.f, 0.f, 0.f};
-	float dL_dpixel[3] = {0.f, 0.f, 0.f};
-	if (inside) {
-		const size_t HW = (size_t)H * W;
-#pragma unroll
-		for (int i = 0; i < 3; i++) dL_dpixel[i] = dL_dpixels[i * HW + pix_id];
-	}
-	float last_alpha = 0;
-	float last_color[3] = {0.f, 0.f, 0.f};
 	const float ddelx_dx = 0.5 * W;
 	const float ddely_dy = 0.5 * H;
-	float bg_dot_dpixel = 0;
-#pragma unroll
-	for (int i = 0; i < 3; i++) bg_dot_dpixel += bg_color[i] * dL_dpixel[i];
 	const int my_slot = ((lane & 1) == 0) ? warp_reduce9_index(lane) : -1;
 	unsigned char* dirty8 = reinterpret_cast<unsigned char*>(sm.dirty);
 
@@ -335,79 +372,88 @@ __global__ void __launch_bounds__(RB) render_bwd_kernel(const uint2* __restrict_
 		const int cnt = min(RBB, n - b * RBB);
 		bool keep = false;
 		if (tid < cnt) keep = splat_reaches_tile(sm.rec[st][tid].q0, sm.rec[st][tid].q1, rx0, ry0, rx1, ry1);
-		const int ccount = compact_block(keep, sm.cidx, sm.wcnt, tid);
+		const int ccount = compact_block<G::NWARPS>(keep, sm.cidx, sm.wcnt, tid);
 
 		for (int c0 = 0; c0 < ccount; c0 += 32) {
-		const int kk = c0 + lane;
-		int jl = 0;
-		bool hit = false;
-		if (kk < ccount) {
-			jl = sm.cidx[kk];
-			// entries behind every pixel's last contributor of this warp cannot receive gradient either
-			hit = (n - 1 - (b * RBB + jl)) < warp_maxc && splat_reaches_tile(sm.rec[st][jl].q0, sm.rec[st][jl].q1, wx0, wy0, wx1, wy1);
-		}
-		uint32_t hits = __ballot_sync(0xffffffffu, hit);
-		while (hits) {
-			const int src = __ffs(hits) - 1;
-			hits &= hits - 1;
-			const int j = __shfl_sync(0xffffffffu, jl, src);
-			// 0-based list position of this entry; the reference's `contributor` after its decrement
-			const int pos = n - 1 - (b * RBB + j);
-			bool active = pos < last_contributor;
-			const float4 q0 = sm.rec[st][j].q0;
-			const float4 q1 = sm.rec[st][j].q1;
-			const float2 xy = make_float2(q0.x, q0.y);
-			const float2 d = make_float2(xy.x - pixf.x, xy.y - pixf.y);
-			const float4 con_o = make_float4(q0.z, q0.w, q1.x, q1.y);
-			const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-			active = active && !(power > 0.0f) && !(power < q1.z);  // q1.z = pmin, see GaussRec
-			float G = 0.f, alpha = 0.f;
-			if (active) {
-				G = exp(power);
-				alpha = min(0.99f, con_o.w * G);
-				active = !(alpha < 1.0f / 255.0f);
+			const int kk = c0 + lane;
+			int jl = 0;
+			bool hit = false;
+			if (kk < ccount) {
+				jl = sm.cidx[kk];
+				// entries behind every pixel's last contributor of this warp cannot receive gradient either
+				hit = (n - 1 - (b * RBB + jl)) < warp_maxc && splat_reaches_tile(sm.rec[st][jl].q0, sm.rec[st][jl].q1, wx0, wy0, wx1, wy1);
 			}
-			if (!__any_sync(0xffffffffu, active)) continue;
-
-			float v[9];
+			uint32_t hits = __ballot_sync(0xffffffffu, hit);
+			while (hits) {
+				const int src = __ffs(hits) - 1;
+				hits &= hits - 1;
+				const int j = __shfl_sync(0xffffffffu, jl, src);
+				// 0-based list position of this entry; the reference's `contributor` after its decrement
+				const int pos = n - 1 - (b * RBB + j);
+				const float4 q0 = sm.rec[st][j].q0;
+				const float4 q1 = sm.rec[st][j].q1;
+				const float2 xy = make_float2(q0.x, q0.y);
+				const float4 con_o = make_float4(q0.z, q0.w, q1.x, q1.y);
+				float2 d[PPT];
+				float G_[PPT], alpha[PPT];
+				bool active[PPT];
+				bool any = false;
 #pragma unroll
-			for (int i = 0; i < 9; i++) v[i] = 0.f;
-			if (active) {
-				T = T / (1.f - alpha);
-				const float dchannel_dcolor = alpha * T;
+				for (int p = 0; p < PPT; p++) {
+					d[p] = make_float2(xy.x - pixfx, xy.y - pixfy[p]);
+					const float power = -0.5f * (con_o.x * d[p].x * d[p].x + con_o.z * d[p].y * d[p].y) - con_o.y * d[p].x * d[p].y;
+					active[p] = pos < last_contributor[p] && !(power > 0.0f) && !(power < q1.z);  // q1.z = pmin, see GaussRec
+					G_[p] = 0.f; alpha[p] = 0.f;
+					if (active[p]) {
+						G_[p] = exp(power);
+						alpha[p] = min(0.99f, con_o.w * G_[p]);
+						active[p] = !(alpha[p] < 1.0f / 255.0f);
+					}
+					any = any || active[p];
+				}
+				if (!__any_sync(0xffffffffu, any)) continue;
+
+				float v[9];
+#pragma unroll
+				for (int i = 0; i < 9; i++) v[i] = 0.f;
 				const float4 q2 = sm.rec[st][j].q2;
 				const float col[3] = {q2.x, q2.y, q2.z};
-				float dL_dalpha = 0.0f;
 #pragma unroll
-				for (int ch = 0; ch < 3; ch++) {
-					const float c = col[ch];
-					accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-					last_color[ch] = c;
-					const float dL_dchannel = dL_dpixel[ch];
-					dL_dalpha += (c - accum_rec[ch]) * dL_dchannel;
-					v[6 + ch] = dchannel_dcolor * dL_dchannel;
-				}
-				dL_dalpha *= T;
-				last_alpha = alpha;
-				dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+				for (int p = 0; p < PPT; p++) {
+					if (!active[p]) continue;
+					T[p] = T[p] / (1.f - alpha[p]);
+					const float dchannel_dcolor = alpha[p] * T[p];
+					float dL_dalpha = 0.0f;
+#pragma unroll
+					for (int ch = 0; ch < 3; ch++) {
+						const float c = col[ch];
+						accum_rec[p][ch] = last_alpha[p] * last_color[p][ch] + (1.f - last_alpha[p]) * accum_rec[p][ch];
+						last_color[p][ch] = c;
+						const float dL_dchannel = dL_dpixel[p][ch];
+						dL_dalpha += (c - accum_rec[p][ch]) * dL_dchannel;
+						v[6 + ch] += dchannel_dcolor * dL_dchannel;
+					}
+					dL_dalpha *= T[p];
+					last_alpha[p] = alpha[p];
+					dL_dalpha += (-T_final[p] / (1.f - alpha[p])) * bg_dot_dpixel[p];
 
-				const float dL_dG = con_o.w * dL_dalpha;
-				const float gdx = G * d.x;
-				const float gdy = G * d.y;
-				const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
-				const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
-				v[0] = dL_dG * dG_ddelx * ddelx_dx;
-				v[1] = dL_dG * dG_ddely * ddely_dy;
-				v[2] = -0.5f * gdx * d.x * dL_dG;
-				v[3] = -0.5f * gdx * d.y * dL_dG;
-				v[4] = -0.5f * gdy * d.y * dL_dG;
-				v[5] = G * dL_dalpha;
+					const float dL_dG = con_o.w * dL_dalpha;
+					const float gdx = G_[p] * d[p].x;
+					const float gdy = G_[p] * d[p].y;
+					const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
+					const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
+					v[0] += dL_dG * dG_ddelx * ddelx_dx;
+					v[1] += dL_dG * dG_ddely * ddely_dy;
+					v[2] += -0.5f * gdx * d[p].x * dL_dG;
+					v[3] += -0.5f * gdx * d[p].y * dL_dG;
+					v[4] += -0.5f * gdy * d[p].y * dL_dG;
+					v[5] += G_[p] * dL_dalpha;
+				}
+				const float tot = warp_reduce9(v, lane);
+				// each (warp, entry) pair is visited once per batch: plain stores, no shared-memory atomics
+				if (my_slot >= 0) sm.acc[j * ACC_ROW + warp * 9 + my_slot] = tot;
+				if (lane == 0) dirty8[j * 8 + warp] = 1;
 			}
-			const float tot = warp_reduce9(v, lane);
-			// each (warp, entry) pair is visited once per batch: plain stores, no shared-memory atomics
-			if (my_slot >= 0) sm.acc[j * ACC_ROW + warp * 9 + my_slot] = tot;
-			if (lane == 0) dirty8[j * 8 + warp] = 1;
-		}
 		}
 		__syncthreads();
 
@@ -420,7 +466,7 @@ __global__ void __launch_bounds__(RB) render_bwd_kernel(const uint2* __restrict_
 #pragma unroll
 				for (int i = 0; i < 9; i++) a[i] = 0.f;
 #pragma unroll
-				for (int w = 0; w < RB / 32; w++) {
+				for (int w = 0; w < G::NWARPS; w++) {
 					if ((dm >> (8 * w)) & 0xffull) {
 #pragma unroll
 						for (int i = 0; i < 9; i++) a[i] += sm.acc[tid * ACC_ROW + w * 9 + i];
@@ -449,11 +495,39 @@ __global__ void __launch_bounds__(RB) render_bwd_kernel(const uint2* __restrict_
 	}
 }
 
+// pixels per thread of the two tile kernels (1, 2 or 4); overridable for experiments: PSB_FWD_PPT / PSB_BWD_PPT
+static int env_ppt(const char* name, int dflt)
+{
+	const char* e = getenv(name);
+	if (!e) return dflt;
+	const int v = atoi(e);
+	return (v == 1 || v == 2 || v == 4) ? v : dflt;
+}
+
+template <int PPT>
+static int launch_bwd_t(const Camera& cam, const uint2* ranges, const uint32_t* point_list, const GaussRec* rec, const float* bg,
+                        const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, const GradSink& sink, cudaStream_t stream)
+{
+	static bool attr_set = false;
+	if (!attr_set) {
+		PSB_CUDA_OK(cudaFuncSetAttribute(render_bwd_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem<PPT>)));
+		attr_set = true;
+	}
+	dim3 grid(cam.grid_x, cam.grid_y, 1);
+	render_bwd_kernel<PPT><<<grid, TileGeom<PPT>::THREADS, sizeof(BwdSmem<PPT>), stream>>>(ranges, point_list, rec, cam.W, cam.H, bg, final_T, n_contrib,
+	                                                                                      dL_dpix, sink);
+	PSB_LAUNCH_OK();
+	return 0;
+}
+
 int launch_render_forward(const Camera& cam, const uint2* ranges, const uint32_t* point_list, const GaussRec* rec, const float* bg,
                           float* out_color, float* final_T, uint32_t* n_contrib, cudaStream_t stream)
 {
+	static const int ppt = env_ppt("PSB_FWD_PPT", 2);
 	dim3 grid(cam.grid_x, cam.grid_y, 1);
-	render_fwd_kernel<<<grid, RB, 0, stream>>>(ranges, point_list, rec, cam.W, cam.H, bg, out_color, final_T, n_contrib);
+	if (ppt == 1) render_fwd_kernel<1><<<grid, TileGeom<1>::THREADS, 0, stream>>>(ranges, point_list, rec, cam.W, cam.H, bg, out_color, final_T, n_contrib);
+	else if (ppt == 2) render_fwd_kernel<2><<<grid, TileGeom<2>::THREADS, 0, stream>>>(ranges, point_list, rec, cam.W, cam.H, bg, out_color, final_T, n_contrib);
+	else render_fwd_kernel<4><<<grid, TileGeom<4>::THREADS, 0, stream>>>(ranges, point_list, rec, cam.W, cam.H, bg, out_color, final_T, n_contrib);
 	PSB_LAUNCH_OK();
 	return 0;
 }
@@ -462,15 +536,10 @@ int launch_render_backward(const Camera& cam, const uint2* ranges, const uint32_
                            const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, const GradSink& sink,
                            cudaStream_t stream)
 {
-	dim3 grid(cam.grid_x, cam.grid_y, 1);
-	static bool attr_set = false;
-	if (!attr_set) {
-		PSB_CUDA_OK(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
-		attr_set = true;
-	}
-	render_bwd_kernel<<<grid, RB, sizeof(BwdSmem), stream>>>(ranges, point_list, rec, cam.W, cam.H, bg, final_T, n_contrib, dL_dpix, sink);
-	PSB_LAUNCH_OK();
-	return 0;
+	static const int ppt = env_ppt("PSB_BWD_PPT", 2);
+	if (ppt == 1) return launch_bwd_t<1>(cam, ranges, point_list, rec, bg, final_T, n_contrib, dL_dpix, sink, stream);
+	if (ppt == 2) return launch_bwd_t<2>(cam, ranges, point_list, rec, bg, final_T, n_contrib, dL_dpix, sink, stream);
+	return launch_bwd_t<4>(cam, ranges, point_list, rec, bg, final_T, n_contrib, dL_dpix, sink, stream);
 }
 
 }  // namespace psb
