@@ -167,6 +167,10 @@ int psb_trainer_backward(psb_trainer* t, int P, int M, const psb_model* model, c
                          float* out_color, int* radii, float* const* grads, void* stream);
 int psb_adam_update(int P, int M, const psb_model* model, float* const* grads, const psb_step* step,
                     float grad_scale, void* stream);
+/* Same update on one flat range of n floats (any slice of a parameter tensor and the matching slices of its moments and
+ * gradient) with an explicit learning rate: lets the caller pipeline chunked all-reduces with the optimizer. */
+int psb_adam_flat(size_t n, float* param, float* exp_avg, float* exp_avg_sq, const float* grad, float lr,
+                  const psb_step* step, float grad_scale, void* stream);
 
 /* Blocks on `stream` and returns the results of the last step / backward / render:
  * out3 = {loss, l1, ssim} (host, may be NULL), *num_rendered (may be NULL).

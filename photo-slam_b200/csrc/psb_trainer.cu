@@ -260,6 +260,14 @@ int psb_adam_update(int P, int M, const psb_model* model, float* const* grads, c
 	return 0;
 }
 
+int psb_adam_flat(size_t n, float* param, float* exp_avg, float* exp_avg_sq, const float* grad, float lr, const psb_step* step,
+                  float grad_scale, void* stream_)
+{
+	if (!step || step->step < 1 || (n > 0 && (!param || !exp_avg || !exp_avg_sq || !grad))) { set_error_msg("psb_adam_flat: bad argument"); return PSB_ERR_ARG; }
+	const StepHyper h = to_hyper(step);
+	return launch_adam(n, param, exp_avg, exp_avg_sq, grad, lr, h, grad_scale, (cudaStream_t)stream_);
+}
+
 int psb_trainer_result(psb_trainer* t, float* out3, int* num_rendered, void* stream_)
 {
 	cudaStream_t stream = (cudaStream_t)stream_;

@@ -288,10 +288,46 @@ class DataParallelTrainer(GaussianTrainer):
                                                gt_image.data_ptr(), mask.data_ptr() if mask is not None else None, C.byref(cs),
                                                out_color.data_ptr() if out_color is not None else None,
                                                radii.data_ptr() if radii is not None else None, ptrs, stream), "psb_trainer_backward")
-        scale = self.grads.all_reduce(self.group)   # ONE collective per step: 59 floats per Gaussian
-        _lib.check(self.L.psb_adam_update(m.num_points(), 16, C.byref(cm), ptrs, C.byref(cs), scale, stream), "psb_adam_update")
+        if self.world == 1:
+            _lib.check(self.L.psb_adam_update(m.num_points(), 16, C.byref(cm), ptrs, C.byref(cs), 1.0, stream), "psb_adam_update")
+        else:
+            self._reduce_and_update(cs)
         m.step_ += 1
         self._last = (cam, gt_image, mask, out_color, radii, densify_stats)
+
+    def _reduce_and_update(self, cs):
+        """All-reduce of the flat [P*59] gradient in chunks on a side stream, pipelined with the Adam update of the chunks
+        that have already arrived (chunk k is being updated while chunk k+1 is still on the NVLink fabric)."""
+        m = self.model
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_comm"):
+            self._comm = torch.cuda.Stream()
+            self.L.psb_adam_flat.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.POINTER(_Step), C.c_float, C.c_void_p]
+            self.L.psb_adam_flat.restype = C.c_int
+            # chunk plan: (tensor index, start, length) — small tensors whole, features_rest in 6 slices
+            self._chunks = []
+            for i, t in enumerate(m.tensors()):
+                n = t.numel()
+                parts = 6 if i == 2 else 1
+                step = (n // parts + 3) // 4 * 4
+                o = 0
+                while o < n:
+                    self._chunks.append((i, o, min(step, n - o)))
+                    o += step
+            self._events = [torch.cuda.Event() for _ in self._chunks]
+        ready = torch.cuda.Event()
+        ready.record(main)
+        scale = 1.0 / self.world
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(ready)
+            for (i, o, n), ev in zip(self._chunks, self._events):
+                self.dist.all_reduce(self.segs[i][o:o + n], op=self.dist.ReduceOp.SUM, group=self.group)
+                ev.record(self._comm)
+        for (i, o, n), ev in zip(self._chunks, self._events):
+            main.wait_event(ev)
+            p, a, b = m.tensors()[i].view(-1), m.exp_avg_[i].view(-1), m.exp_avg_sq_[i].view(-1)
+            _lib.check(self.L.psb_adam_flat(n, p[o:].data_ptr(), a[o:].data_ptr(), b[o:].data_ptr(), self.segs[i][o:].data_ptr(), m.lr_[i],
+                                            C.byref(cs), scale, main.cuda_stream), "psb_adam_flat")
 
     def sync_densify_stats(self):
         """Reduce the rank-local densification statistics (call right before densify/prune)."""
