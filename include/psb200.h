@@ -167,6 +167,17 @@ int psb_trainer_backward(psb_trainer* t, int P, int M, const psb_model* model, c
                          float* out_color, int* radii, float* const* grads, void* stream);
 int psb_adam_update(int P, int M, const psb_model* model, float* const* grads, const psb_step* step,
                     float grad_scale, void* stream);
+/* Pipelined form of psb_trainer_backward: _begin runs render, loss and the tile backward (everything up to the 9
+ * screen-space sums per Gaussian); _slab then produces the raw-parameter gradients of Gaussians [first, first+count)
+ * (first a multiple of 128). grads[i] must point at the address where row 0 of tensor i WOULD be, i.e.
+ * slab_buffer_i - first * floats_per_row_i: the kernel writes row g of tensor i at grads[i] + g * floats_per_row_i,
+ * which lets the caller keep each slab's six gradient blocks contiguous and all-reduce slab k while slab k+1 is
+ * still being computed. */
+int psb_trainer_backward_begin(psb_trainer* t, int P, int M, const psb_model* model, const psb_camera* camera,
+                               const float* background, const float* gt_image, const float* mask, const psb_step* step,
+                               float* out_color, int* radii, void* stream);
+int psb_trainer_backward_slab(psb_trainer* t, int P, int M, const psb_model* model, const psb_camera* camera,
+                              const psb_step* step, int first, int count, float* const* grads, void* stream);
 /* Same update on one flat range of n floats (any slice of a parameter tensor and the matching slices of its moments and
  * gradient) with an explicit learning rate: lets the caller pipeline chunked all-reduces with the optimizer. */
 int psb_adam_flat(size_t n, float* param, float* exp_avg, float* exp_avg_sq, const float* grad, float lr,

@@ -57,7 +57,7 @@ __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, flo
 // bulk copy per block. Phase 2 (whole block, element-wise, 128-bit coalesced): Adam over the block's
 // [128 x 45] f_rest chunk, gradient looked up from the seeds in shared memory.
 template <bool ADAM>
-__global__ void __launch_bounds__(TB, 5) fused_backward_kernel(int P, TrainTensors t, Camera cam, GeomState geom, float4* __restrict__ sink,
+__global__ void __launch_bounds__(TB, 5) fused_backward_kernel(int first, int P, TrainTensors t, Camera cam, GeomState geom, float4* __restrict__ sink,
                                                             StepHyper h, GradSegments grads, DensifyStats st,
                                                             const uint32_t* __restrict__ counters, uint32_t capacity)
 {
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(TB, 5) fused_backward_kernel(int P, TrainTenso
 	if (counters[0] > capacity) return;
 
 	const int tid = threadIdx.x;
-	const int base = blockIdx.x * TB;
+	const int base = first + blockIdx.x * TB;  // this launch covers Gaussians [first, P)
 	const int rows = min(TB, P - base);
 	const uint32_t row_bytes = (uint32_t)rows * REST * sizeof(float);
 	const uint32_t bulk_bytes = row_bytes & ~15u;
@@ -300,15 +300,15 @@ __global__ void adam_tail_kernel(size_t start, size_t n, float* p, float* m, flo
 
 size_t fused_backward_smem_bytes(bool) { return 0; }  // static shared memory only
 
-int launch_fused_backward(bool adam, int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, const StepHyper& h,
+int launch_fused_backward(bool adam, int first, int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, const StepHyper& h,
                           const GradSegments& grads, const DensifyStats& st, const uint32_t* counters, uint32_t capacity, cudaStream_t stream)
 {
-	if (P == 0) return 0;
-	const int grid = cdiv(P, TB);
+	if (P - first <= 0) return 0;
+	const int grid = cdiv(P - first, TB);
 	if (adam)
-		fused_backward_kernel<true><<<grid, TB, 0, stream>>>(P, t, cam, geom, reinterpret_cast<float4*>(sink), h, grads, st, counters, capacity);
+		fused_backward_kernel<true><<<grid, TB, 0, stream>>>(first, P, t, cam, geom, reinterpret_cast<float4*>(sink), h, grads, st, counters, capacity);
 	else
-		fused_backward_kernel<false><<<grid, TB, 0, stream>>>(P, t, cam, geom, reinterpret_cast<float4*>(sink), h, grads, st, counters, capacity);
+		fused_backward_kernel<false><<<grid, TB, 0, stream>>>(first, P, t, cam, geom, reinterpret_cast<float4*>(sink), h, grads, st, counters, capacity);
 	PSB_LAUNCH_OK();
 	return 0;
 }

@@ -161,11 +161,12 @@ int forward_raw(psb_trainer* t, int P, int M, int D, const psb_model* model, con
 }
 
 int step_impl(psb_trainer* t, int P, int M, const psb_model* model, const psb_camera* camera, const float* background, const float* gt_image,
-              const float* mask, const psb_step* step, float* out_color, int* radii, float* const* grads, cudaStream_t stream)
+              const float* mask, const psb_step* step, float* out_color, int* radii, float* const* grads, cudaStream_t stream,
+              bool tiles_only = false)
 {
 	int rc;
 	if (!t || !camera || !step || !background || !gt_image) { set_error_msg("psb_trainer_step: null argument"); return PSB_ERR_ARG; }
-	if ((rc = check_model(P, M, model, grads == nullptr))) return rc;
+	if ((rc = check_model(P, M, model, grads == nullptr && !tiles_only))) return rc;
 	if (step->sh_degree < 0 || step->sh_degree > 3 || step->step < 1) { set_error_msg("psb_trainer_step: sh_degree in 0..3 and step >= 1 required"); return PSB_ERR_ARG; }
 	GeomState geom; BinState bin; ImgState img; Camera cam;
 	if ((rc = forward_raw(t, P, M, step->sh_degree, model, camera, background, out_color, radii, geom, bin, img, cam, stream))) return rc;
@@ -184,6 +185,7 @@ int step_impl(psb_trainer* t, int P, int M, const psb_model* model, const psb_ca
 	const int res = make_sort_plan(tile_id_bits(cam.grid_x * cam.grid_y)).npass & 1;
 	if ((rc = launch_render_backward(cam, img.ranges, bin.inst[res], geom.rec, background, img.final_T, img.n_contrib, t->dL_dpix, sink, stream))) return rc;
 	t->mark(6, stream);
+	if (tiles_only) return 0;
 	TrainTensors tt;
 	for (int i = 0; i < 6; i++) { tt.p[i] = model->param[i]; tt.m[i] = model->exp_avg[i]; tt.v[i] = model->exp_avg_sq[i]; }
 	GradSegments gs;
@@ -192,7 +194,7 @@ int step_impl(psb_trainer* t, int P, int M, const psb_model* model, const psb_ca
 	st.enabled = (step->update_densify_stats && model->max_radii2D && model->xyz_gradient_accum && model->denom) ? 1 : 0;
 	st.max_radii2D = model->max_radii2D; st.xyz_gradient_accum = model->xyz_gradient_accum; st.denom = model->denom;
 	const StepHyper h = to_hyper(step);
-	rc = launch_fused_backward(grads == nullptr, P, tt, cam, geom, t->sink, h, gs, st, geom.counters, (uint32_t)t->capacity, stream);
+	rc = launch_fused_backward(grads == nullptr, 0, P, tt, cam, geom, t->sink, h, gs, st, geom.counters, (uint32_t)t->capacity, stream);
 	t->mark(7, stream);
 	t->ev_recorded = t->profiling && t->ev_ready;
 	return rc;
@@ -244,6 +246,34 @@ int psb_trainer_backward(psb_trainer* t, int P, int M, const psb_model* model, c
 	if (!grads) { set_error_msg("psb_trainer_backward: grads required"); return PSB_ERR_ARG; }
 	for (int i = 0; i < 6; i++) if (P > 0 && !grads[i]) { set_error_msg("psb_trainer_backward: null gradient segment"); return PSB_ERR_ARG; }
 	return step_impl(t, P, M, model, camera, background, gt_image, mask, step, out_color, radii, grads, (cudaStream_t)stream_);
+}
+
+int psb_trainer_backward_begin(psb_trainer* t, int P, int M, const psb_model* model, const psb_camera* camera, const float* background,
+                               const float* gt_image, const float* mask, const psb_step* step, float* out_color, int* radii, void* stream_)
+{
+	return step_impl(t, P, M, model, camera, background, gt_image, mask, step, out_color, radii, nullptr, (cudaStream_t)stream_, /*tiles_only=*/true);
+}
+
+int psb_trainer_backward_slab(psb_trainer* t, int P, int M, const psb_model* model, const psb_camera* camera, const psb_step* step, int first,
+                              int count, float* const* grads, void* stream_)
+{
+	int rc;
+	if (!t || !camera || !step || !grads || t->geom_P != P) { set_error_msg("psb_trainer_backward_slab: bad argument / no matching backward_begin"); return PSB_ERR_ARG; }
+	if ((rc = check_model(P, M, model, false))) return rc;
+	if (first < 0 || count < 0 || first + count > P || (first % 128) != 0) { set_error_msg("psb_trainer_backward_slab: slab must start at a multiple of 128"); return PSB_ERR_ARG; }
+	if (count == 0) return 0;
+	char* gc = t->geom_chunk;
+	GeomState geom = GeomState::from_chunk(gc, (size_t)P);
+	const Camera cam = to_camera(camera);
+	TrainTensors tt;
+	for (int i = 0; i < 6; i++) { tt.p[i] = model->param[i]; tt.m[i] = nullptr; tt.v[i] = nullptr; }
+	GradSegments gs;
+	for (int i = 0; i < 6; i++) gs.g[i] = grads[i];
+	DensifyStats st;
+	st.enabled = (step->update_densify_stats && model->max_radii2D && model->xyz_gradient_accum && model->denom) ? 1 : 0;
+	st.max_radii2D = model->max_radii2D; st.xyz_gradient_accum = model->xyz_gradient_accum; st.denom = model->denom;
+	const StepHyper h = to_hyper(step);
+	return launch_fused_backward(false, first, first + count, tt, cam, geom, t->sink, h, gs, st, geom.counters, (uint32_t)t->capacity, (cudaStream_t)stream_);
 }
 
 int psb_adam_update(int P, int M, const psb_model* model, float* const* grads, const psb_step* step, float grad_scale, void* stream_)

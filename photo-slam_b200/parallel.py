@@ -48,3 +48,38 @@ def reduce_densify_stats(max_radii2D, xyz_gradient_accum, denom, group=None):
         dist.all_reduce(max_radii2D, op=dist.ReduceOp.MAX, group=group)
         dist.all_reduce(xyz_gradient_accum, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(denom, op=dist.ReduceOp.SUM, group=group)
+
+
+class SlabGradBuffer:
+    """The same [P*59] floats, laid out slab-major: Gaussians are cut into `nslabs` contiguous ranges (boundaries at
+    multiples of 128) and each slab keeps its six gradient blocks back to back, so ONE all-reduce call per slab covers
+    all parameters of those Gaussians and can start as soon as the slab's backward kernel has finished."""
+
+    def __init__(self, P, device, nslabs=4):
+        self.P = P
+        self.flat = torch.zeros(max(P, 1) * PER_GAUSSIAN, dtype=torch.float32, device=device)
+        per = -(-P // nslabs)
+        per = -(-per // 128) * 128
+        self.slabs = []           # (first, count)
+        f = 0
+        while f < P:
+            self.slabs.append((f, min(per, P - f)))
+            f += per
+
+    def region(self, s):
+        first, count = self.slabs[s]
+        return self.flat[first * PER_GAUSSIAN:(first + count) * PER_GAUSSIAN]
+
+    def blocks(self, s):
+        """Six 1-D views (one per parameter tensor) of slab s."""
+        first, count = self.slabs[s]
+        out, o = [], first * PER_GAUSSIAN
+        for k in SIZES:
+            out.append(self.flat[o:o + count * k])
+            o += count * k
+        return out
+
+    def kernel_pointers(self, s):
+        """Base addresses such that row g of tensor i lands at blocks(s)[i][(g - first) * SIZES[i]] (see psb_trainer_backward_slab)."""
+        first, _ = self.slabs[s]
+        return [b.data_ptr() - first * k * 4 for b, k in zip(self.blocks(s), SIZES)]

@@ -262,19 +262,40 @@ class GaussianTrainer:
 
 
 class DataParallelTrainer(GaussianTrainer):
-    """Keyframe-sharded data parallelism: replicated Gaussians, rank r renders its own view,
-    ONE all-reduce (sum) over the flat [P*59] raw-parameter gradient buffer, then the same Adam update on
-    every rank with grad_scale = 1/world (mean over views keeps the learning-rate scale of one view per step)."""
+    """Keyframe-sharded data parallelism: replicated Gaussians, rank r renders its own view, the flat
+    [P*59] raw-parameter gradient is summed over ranks, then every rank applies the same Adam update with
+    grad_scale = 1/world (mean over the K views of the step keeps the learning-rate scale of one view per step).
 
-    def __init__(self, model, opt=None, background=None, group=None):
+    world == 1 (or pipeline=False): backward -> one all-reduce -> Adam.
+    world  > 1 (or pipeline=True): the per-Gaussian backward runs slab by slab; slab k is all-reduced on a side stream
+    (NCCL over NVLink) while the kernel of slab k+1 runs, and its Adam update is issued as soon as its sum has arrived."""
+
+    def __init__(self, model, opt=None, background=None, group=None, pipeline=None, nslabs=4):
         super().__init__(model, opt, background)
         import torch.distributed as dist
+        from .parallel import GradBuffer, SlabGradBuffer
         self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        from .parallel import GradBuffer
-        self.grads = GradBuffer(model.num_points(), model.device)
-        self.flat, self.segs = self.grads.flat, self.grads.segments
+        self.pipeline = (self.world > 1) if pipeline is None else bool(pipeline)
+        P = model.num_points()
+        if self.pipeline:
+            self.grads = SlabGradBuffer(P, model.device, nslabs)
+            self._comm = torch.cuda.Stream()
+            n = len(self.grads.slabs)
+            self._ev_k = [torch.cuda.Event() for _ in range(n)]
+            self._ev_c = [torch.cuda.Event() for _ in range(n)]
+            vp = C.c_void_p
+            self.L.psb_trainer_backward_begin.argtypes = [vp, C.c_int, C.c_int, C.POINTER(_Model), C.POINTER(_Camera), vp, vp, vp, C.POINTER(_Step), vp, vp, vp]
+            self.L.psb_trainer_backward_slab.argtypes = [vp, C.c_int, C.c_int, C.POINTER(_Model), C.POINTER(_Camera), C.POINTER(_Step), C.c_int, C.c_int,
+                                                         C.POINTER(vp), vp]
+            self.L.psb_adam_flat.argtypes = [C.c_size_t, vp, vp, vp, vp, C.c_float, C.POINTER(_Step), C.c_float, vp]
+            for nme in ("psb_trainer_backward_begin", "psb_trainer_backward_slab", "psb_adam_flat"):
+                getattr(self.L, nme).restype = C.c_int
+        else:
+            self.grads = GradBuffer(P, model.device)
+            self.segs = self.grads.segments
+        self.flat = self.grads.flat
 
     def trainForOneIteration(self, cam, gt_image, mask=None, out_color=None, radii=None, densify_stats=None):
         m = self.model
@@ -282,52 +303,41 @@ class DataParallelTrainer(GaussianTrainer):
         if densify_stats is None:
             densify_stats = self.iteration < self.opt.densify_until_iter
         cm, cc, cs = m._cmodel(), _ccamera(cam), self._cstep(densify_stats)
-        ptrs = (C.c_void_p * 6)(*[s.data_ptr() for s in self.segs])
-        stream = torch.cuda.current_stream().cuda_stream
-        _lib.check(self.L.psb_trainer_backward(self.h, m.num_points(), 16, C.byref(cm), C.byref(cc), self.background.data_ptr(),
-                                               gt_image.data_ptr(), mask.data_ptr() if mask is not None else None, C.byref(cs),
-                                               out_color.data_ptr() if out_color is not None else None,
-                                               radii.data_ptr() if radii is not None else None, ptrs, stream), "psb_trainer_backward")
-        if self.world == 1:
-            _lib.check(self.L.psb_adam_update(m.num_points(), 16, C.byref(cm), ptrs, C.byref(cs), 1.0, stream), "psb_adam_update")
+        main = torch.cuda.current_stream()
+        stream = main.cuda_stream
+        P = m.num_points()
+        args = (self.h, P, 16, C.byref(cm), C.byref(cc), self.background.data_ptr(), gt_image.data_ptr(),
+                mask.data_ptr() if mask is not None else None, C.byref(cs), out_color.data_ptr() if out_color is not None else None,
+                radii.data_ptr() if radii is not None else None)
+        if not self.pipeline:
+            ptrs = (C.c_void_p * 6)(*[s.data_ptr() for s in self.segs])
+            _lib.check(self.L.psb_trainer_backward(*args, ptrs, stream), "psb_trainer_backward")
+            scale = self.grads.all_reduce(self.group)   # ONE collective per step: 59 floats per Gaussian
+            _lib.check(self.L.psb_adam_update(P, 16, C.byref(cm), ptrs, C.byref(cs), scale, stream), "psb_adam_update")
         else:
-            self._reduce_and_update(cs)
+            from .parallel import SIZES
+            _lib.check(self.L.psb_trainer_backward_begin(*args, stream), "psb_trainer_backward_begin")
+            scale = 1.0 / self.world
+            for s, (first, count) in enumerate(self.grads.slabs):
+                ptrs = (C.c_void_p * 6)(*self.grads.kernel_pointers(s))
+                _lib.check(self.L.psb_trainer_backward_slab(self.h, P, 16, C.byref(cm), C.byref(cc), C.byref(cs), first, count, ptrs, stream),
+                           "psb_trainer_backward_slab")
+                if self.world > 1:
+                    self._ev_k[s].record(main)
+                    with torch.cuda.stream(self._comm):
+                        self._comm.wait_event(self._ev_k[s])
+                        self.dist.all_reduce(self.grads.region(s), op=self.dist.ReduceOp.SUM, group=self.group)
+                        self._ev_c[s].record(self._comm)
+            for s, (first, count) in enumerate(self.grads.slabs):
+                if self.world > 1:
+                    main.wait_event(self._ev_c[s])
+                for i, (blk, k) in enumerate(zip(self.grads.blocks(s), SIZES)):
+                    p, a, b = m.tensors()[i].view(-1), m.exp_avg_[i].view(-1), m.exp_avg_sq_[i].view(-1)
+                    o = first * k
+                    _lib.check(self.L.psb_adam_flat(count * k, p[o:].data_ptr(), a[o:].data_ptr(), b[o:].data_ptr(), blk.data_ptr(), m.lr_[i],
+                                                    C.byref(cs), scale, stream), "psb_adam_flat")
         m.step_ += 1
         self._last = (cam, gt_image, mask, out_color, radii, densify_stats)
-
-    def _reduce_and_update(self, cs):
-        """All-reduce of the flat [P*59] gradient in chunks on a side stream, pipelined with the Adam update of the chunks
-        that have already arrived (chunk k is being updated while chunk k+1 is still on the NVLink fabric)."""
-        m = self.model
-        main = torch.cuda.current_stream()
-        if not hasattr(self, "_comm"):
-            self._comm = torch.cuda.Stream()
-            self.L.psb_adam_flat.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.POINTER(_Step), C.c_float, C.c_void_p]
-            self.L.psb_adam_flat.restype = C.c_int
-            # chunk plan: (tensor index, start, length) — small tensors whole, features_rest in 6 slices
-            self._chunks = []
-            for i, t in enumerate(m.tensors()):
-                n = t.numel()
-                parts = 6 if i == 2 else 1
-                step = (n // parts + 3) // 4 * 4
-                o = 0
-                while o < n:
-                    self._chunks.append((i, o, min(step, n - o)))
-                    o += step
-            self._events = [torch.cuda.Event() for _ in self._chunks]
-        ready = torch.cuda.Event()
-        ready.record(main)
-        scale = 1.0 / self.world
-        with torch.cuda.stream(self._comm):
-            self._comm.wait_event(ready)
-            for (i, o, n), ev in zip(self._chunks, self._events):
-                self.dist.all_reduce(self.segs[i][o:o + n], op=self.dist.ReduceOp.SUM, group=self.group)
-                ev.record(self._comm)
-        for (i, o, n), ev in zip(self._chunks, self._events):
-            main.wait_event(ev)
-            p, a, b = m.tensors()[i].view(-1), m.exp_avg_[i].view(-1), m.exp_avg_sq_[i].view(-1)
-            _lib.check(self.L.psb_adam_flat(n, p[o:].data_ptr(), a[o:].data_ptr(), b[o:].data_ptr(), self.segs[i][o:].data_ptr(), m.lr_[i],
-                                            C.byref(cs), scale, main.cuda_stream), "psb_adam_flat")
 
     def sync_densify_stats(self):
         """Reduce the rank-local densification statistics (call right before densify/prune)."""

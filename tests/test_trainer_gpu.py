@@ -129,7 +129,8 @@ def test_fused_step_equals_split_path_and_tracks_reference(cuda):
     split_model = trainer.GaussianModel.from_numpy(sc, cuda)
     for m in (fused_model, split_model):
         m.trainingSetup(trainer.GaussianOptimizationParams())
-    fused, split = trainer.GaussianTrainer(fused_model), trainer.DataParallelTrainer(split_model)
+    # split path in its pipelined (slab-wise) form: the code path bench.py --gpus N runs, minus the NCCL calls
+    fused, split = trainer.GaussianTrainer(fused_model), trainer.DataParallelTrainer(split_model, pipeline=True, nslabs=3)
     losses = []
     for it in range(25):
         lr, img_r, _ = ref.train_for_one_iteration(c, gt)
