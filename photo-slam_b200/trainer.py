@@ -88,6 +88,7 @@ class GaussianModel:
         self.lr_ = [0.0] * 6
         self.step_ = 0
         self.lr_delay_steps_ = 0
+        self.percent_dense_ = 0.01
 
     @classmethod
     def from_numpy(cls, scene, device="cuda", sh_degree=3):
@@ -106,6 +107,7 @@ class GaussianModel:
 
     # --- reference GaussianModel::trainingSetup (gaussian_model.cpp:477-509)
     def trainingSetup(self, args: GaussianOptimizationParams):
+        self.percent_dense_ = args.percent_dense
         P = self.num_points()
         z = lambda *s: torch.zeros(s, dtype=torch.float32, device=self.device)
         self.xyz_gradient_accum_, self.denom_, self.max_radii2D_ = z(P, 1), z(P, 1), z(P)
@@ -143,6 +145,110 @@ class GaussianModel:
     def oneUpShDegree(self):
         if self.active_sh_degree_ < self.max_sh_degree_:
             self.active_sh_degree_ += 1
+
+    # ------------------------------------------------------------------------------------------------------------
+    # Densification / pruning / insertion. These are NOT on the per-iteration hot path (every 100 iterations /
+    # per keyframe); like the reference they are tensor surgery with framework ops on the device, mirrored call for
+    # call, on this model's tensors and Adam moments (the reference edits torch::optim::Adam's state in place).
+    # ------------------------------------------------------------------------------------------------------------
+    def getOpacityActivation(self): return torch.sigmoid(self.opacity_)
+    def getScalingActivation(self): return torch.exp(self.scaling_)
+    def getRotationActivation(self): return torch.nn.functional.normalize(self.rotation_)
+
+    def _set(self, tensors):
+        (self.xyz_, self.features_dc_, self.features_rest_, self.opacity_, self.scaling_, self.rotation_) = tensors
+
+    def resetOpacity(self):
+        """reference gaussian_model.cpp:556-565. NOTE: the reference's misplaced parenthesis makes this
+        min(sigmoid(o), 1) — it does NOT clamp to 0.01; only the opacity moments are zeroed."""
+        act = self.getOpacityActivation()
+        new = torch.min(act, torch.ones_like(act * 0.01))
+        self.opacity_ = torch.log(new / (1 - new)).contiguous()      # inverse_sigmoid
+        self.exp_avg_[3] = torch.zeros_like(self.opacity_)
+        self.exp_avg_sq_[3] = torch.zeros_like(self.opacity_)
+
+    def prunePoints(self, mask):
+        """reference gaussian_model.cpp:588-642"""
+        valid = ~mask
+        self._set([t[valid].contiguous() for t in self.tensors()])
+        self.exp_avg_ = [t[valid].contiguous() for t in self.exp_avg_]
+        self.exp_avg_sq_ = [t[valid].contiguous() for t in self.exp_avg_sq_]
+        self.xyz_gradient_accum_ = self.xyz_gradient_accum_[valid].contiguous()
+        self.denom_ = self.denom_[valid].contiguous()
+        self.max_radii2D_ = self.max_radii2D_[valid].contiguous()
+
+    def densificationPostfix(self, new_xyz, new_features_dc, new_features_rest, new_opacities, new_scaling, new_rotation):
+        """reference gaussian_model.cpp:644-714: parameters concatenated, moments zero-extended, statistics reset."""
+        ext = [new_xyz, new_features_dc, new_features_rest, new_opacities, new_scaling, new_rotation]
+        self._set([torch.cat((t, e), dim=0).contiguous() for t, e in zip(self.tensors(), ext)])
+        self.exp_avg_ = [torch.cat((t, torch.zeros_like(e)), dim=0).contiguous() for t, e in zip(self.exp_avg_, ext)]
+        self.exp_avg_sq_ = [torch.cat((t, torch.zeros_like(e)), dim=0).contiguous() for t, e in zip(self.exp_avg_sq_, ext)]
+        P = self.num_points()
+        z = lambda *sh: torch.zeros(sh, dtype=torch.float32, device=self.device)
+        self.xyz_gradient_accum_, self.denom_, self.max_radii2D_ = z(P, 1), z(P, 1), z(P)
+
+    @staticmethod
+    def build_rotation(r):
+        """reference include/general_utils.h:31-56"""
+        q = r / torch.sqrt((r * r).sum(dim=1, keepdim=True))
+        w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        R = torch.zeros((q.size(0), 3, 3), device=r.device)
+        R[:, 0, 0] = 1 - 2 * (y * y + z * z); R[:, 0, 1] = 2 * (x * y - w * z); R[:, 0, 2] = 2 * (x * z + w * y)
+        R[:, 1, 0] = 2 * (x * y + w * z); R[:, 1, 1] = 1 - 2 * (x * x + z * z); R[:, 1, 2] = 2 * (y * z - w * x)
+        R[:, 2, 0] = 2 * (x * z - w * y); R[:, 2, 1] = 2 * (y * z + w * x); R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+        return R
+
+    def densifyAndSplit(self, grads, grad_threshold, scene_extent, N=2, generator=None):
+        """reference gaussian_model.cpp:716-761"""
+        n_init = self.num_points()
+        padded = torch.zeros(n_init, device=self.device)
+        padded[:grads.size(0)] = grads.squeeze()
+        sel = (padded >= grad_threshold) & (self.getScalingActivation().max(dim=1).values > self.percent_dense_ * scene_extent)
+        stds = self.getScalingActivation()[sel].repeat(N, 1)
+        samples = torch.normal(torch.zeros_like(stds), stds, generator=generator)
+        rots = self.build_rotation(self.rotation_[sel]).repeat(N, 1, 1)
+        new_xyz = torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1) + self.xyz_[sel].repeat(N, 1)
+        new_scaling = torch.log(self.getScalingActivation()[sel].repeat(N, 1) / (0.8 * N))
+        self.densificationPostfix(new_xyz, self.features_dc_[sel].repeat(N, 1, 1), self.features_rest_[sel].repeat(N, 1, 1),
+                                  self.opacity_[sel].repeat(N, 1), new_scaling, self.rotation_[sel].repeat(N, 1))
+        prune_filter = torch.cat((sel, torch.zeros(N * int(sel.sum().item()), dtype=torch.bool, device=self.device)))
+        self.prunePoints(prune_filter)
+
+    def densifyAndClone(self, grads, grad_threshold, scene_extent):
+        """reference gaussian_model.cpp:763-793"""
+        sel = (torch.norm(grads, dim=-1) >= grad_threshold) & (self.getScalingActivation().max(dim=1).values <= self.percent_dense_ * scene_extent)
+        self.densificationPostfix(self.xyz_[sel], self.features_dc_[sel], self.features_rest_[sel], self.opacity_[sel], self.scaling_[sel],
+                                  self.rotation_[sel])
+
+    def densifyAndPrune(self, max_grad, min_opacity, extent, max_screen_size, generator=None):
+        """reference gaussian_model.cpp:795-815"""
+        grads = self.xyz_gradient_accum_ / self.denom_
+        grads[grads.isnan()] = 0.0
+        self.densifyAndClone(grads, max_grad, extent)
+        self.densifyAndSplit(grads, max_grad, extent, generator=generator)
+        prune_mask = (self.getOpacityActivation() < min_opacity).squeeze()
+        if max_screen_size:
+            big_vs = self.max_radii2D_ > max_screen_size
+            big_ws = self.getScalingActivation().max(dim=1).values > 0.1 * extent
+            prune_mask = prune_mask | big_vs | big_ws
+        self.prunePoints(prune_mask)
+
+    def increasePcd(self, points, colors):
+        """reference gaussian_model.cpp:193-290: new Gaussians from sparse points — RGB2SH colour, scale from the
+        3-NN mean distance (distCUDA2 = psb_dist_cuda2), identity rotation, opacity = logit(0.1)."""
+        from .points import distCUDA2
+        if points.numel() == 0:
+            return
+        pts = points.to(self.device, torch.float32).contiguous()
+        M = (self.max_sh_degree_ + 1) ** 2
+        f_dc = ((colors.to(self.device, torch.float32) - 0.5) / 0.28209479177387814).unsqueeze(1).contiguous()
+        f_rest = torch.zeros((pts.size(0), M - 1, 3), device=self.device)
+        dist2 = torch.clamp_min(distCUDA2(pts.clone()), 0.0000001)
+        scales = torch.log(torch.sqrt(dist2)).unsqueeze(1).repeat(1, 3)
+        rots = torch.zeros((pts.size(0), 4), device=self.device)
+        rots[:, 0] = 1
+        opac = torch.full((pts.size(0), 1), math.log(0.1 / 0.9), device=self.device)
+        self.densificationPostfix(pts, f_dc, f_rest, opac, scales, rots)
 
     def _cmodel(self, with_state=True):
         m = _Model()
