@@ -35,7 +35,7 @@ import photo_slam_b200.synthetic as syn  # noqa: E402
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="psb", choices=["psb", "reference"])
     ap.add_argument("--points", type=int, default=3_000_000)
@@ -62,7 +62,7 @@ class ClockSampler:
                     self.samples.append([x.strip() for x in o.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def __enter__(self):
         self.t.start()
