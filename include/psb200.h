@@ -223,6 +223,19 @@ int psb_scale_transform_points(int P, float scale, const float* points, const fl
                                const unsigned char* mask, float* out_points, float* out_rots,
                                int fix_quaternion_write, void* stream);
 
+/* Depth image -> camera-space points for masked pixels (idx = v * width + u). Replaces the reproject_depths_pinhole
+ * kernel behind reprojectDepthPinhole (src/stereo_vision.cu:39-61, 138-166). points [P,3] must be zero-initialised. */
+int psb_reproject_depth_pinhole(int P, int width, float fx, float fy, float cx, float cy, const float* depths,
+                                const unsigned char* mask, float* points, void* stream);
+
+/* Keypoints with a 3-D point keep it; the others borrow the depth of the nearest keypoint (squared pixel distance
+ * <= max_pixel_dist) that has one and are re-projected, or get z = -1. Replaces the kernel behind
+ * monocularPinholeInactiveGeoDensifyBySearchingNeighborhoodKeypoints (src/stereo_vision.cu:63-136, 168-215), including
+ * its colour indexing `colors[(int)(v * width + u) + c]`. Outputs [N,3], zero-initialised by the caller. */
+int psb_neighbour_depth_pinhole(int N, int width, float fx, float fy, float cx, float cy, float max_pixel_dist,
+                                const float* pixels, const unsigned char* has3D, const float* points_local,
+                                const float* colors, float* out_points, float* out_colors, void* stream);
+
 /* Standalone sort primitive (tests): stable LSD radix sort of (u32 key, u32 value) pairs on key bits
  * [0, nbits). keys/vals are device arrays of n elements, sorted in place. */
 int psb_debug_sort_pairs(uint32_t* keys, uint32_t* vals, size_t n, int nbits, void* stream);

@@ -196,6 +196,66 @@ __global__ void scale_transform_points_kernel(int P, float scale, const float* _
 	else out_rots[4 * i + 2] = q[2];  // the reference writes z into slot +2 and never writes slot +3 (operate_points.h:170-178)
 }
 
+// (u, v, depth) -> camera-space point; u, v truncated to int like the reference helper
+// (cuda_rasterizer/stereo_vision.h:40-55 takes `const int u, const int v`).
+__device__ __forceinline__ float3 reproject_pinhole(int u, int v, float depth, float fx, float fy, float cx, float cy)
+{
+	return make_float3((u - cx) * depth / fx, (v - cy) * depth / fy, depth);
+}
+
+__global__ void reproject_depths_kernel(int P, int width, float fx, float fy, float cx, float cy, const float* __restrict__ depths,
+                                        const uint8_t* __restrict__ mask, float* __restrict__ points)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= P || !mask[idx]) return;
+	const int v = idx / width, u = idx - v * width;
+	const float3 p = reproject_pinhole(u, v, depths[idx], fx, fy, cx, cy);
+	points[3 * idx] = p.x; points[3 * idx + 1] = p.y; points[3 * idx + 2] = p.z;
+}
+
+// Keypoints without a 3-D point borrow the depth of the nearest keypoint (in pixels) that has one. One warp per
+// keypoint scans the N candidates cooperatively (the reference runs an O(N) loop per thread); ties on the distance keep
+// the lowest index like the reference's strict `dist >= min_dist` rejection.
+__global__ void neighbour_depth_kernel(int N, int width, float fx, float fy, float cx, float cy, float max_pixel_dist,
+                                       const float* __restrict__ pixels, const uint8_t* __restrict__ has3D, const float* __restrict__ p3d,
+                                       const float* __restrict__ colors, float* __restrict__ out_p3d, float* __restrict__ out_col)
+{
+	const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (idx >= N) return;
+	const float u = pixels[2 * idx], v = pixels[2 * idx + 1];
+	const int pix = (int)(v * width + u);  // reference: `int pxidx_in_image = v * width + u;` (src/stereo_vision.cu:86)
+	if (has3D[idx]) {
+		if (lane < 3) { out_p3d[3 * idx + lane] = p3d[3 * idx + lane]; out_col[3 * idx + lane] = colors[pix + lane]; }
+		return;
+	}
+	float best = 3.402823466e+38f;
+	int best_i = 0x7fffffff;
+	for (int i = lane; i < N; i += 32) {
+		if (!has3D[i] || i == idx) continue;
+		const float du = u - pixels[2 * i], dv = v - pixels[2 * i + 1];
+		const float dist = du * du + dv * dv;
+		if (dist > max_pixel_dist) continue;
+		if (dist < best) { best = dist; best_i = i; }  // ascending i within a lane: first minimum kept
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+		const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+		if (ob < best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+	}
+	if (lane == 0) {
+		const float depth = (best_i != 0x7fffffff) ? p3d[3 * best_i + 2] : -1.0f;
+		if (depth > 0.0f) {
+			const float3 p = reproject_pinhole((int)u, (int)v, depth, fx, fy, cx, cy);
+			out_p3d[3 * idx] = p.x; out_p3d[3 * idx + 1] = p.y; out_p3d[3 * idx + 2] = p.z;
+			out_col[3 * idx] = colors[pix]; out_col[3 * idx + 1] = colors[pix + 1]; out_col[3 * idx + 2] = colors[pix + 2];
+		} else {
+			out_p3d[3 * idx + 2] = -1.0f;
+		}
+	}
+}
+
 __global__ void init_bounds_kernel(uint32_t* bounds)
 {
 	if (threadIdx.x < 3) bounds[threadIdx.x] = 0xFFFFFFFFu;
@@ -244,6 +304,28 @@ int psb_dist_cuda2(int P, const float* points, float* mean_dists, void* stream_)
 	}
 	cudaFreeAsync(mem, stream);
 	return rc;
+}
+
+int psb_reproject_depth_pinhole(int P, int width, float fx, float fy, float cx, float cy, const float* depths, const unsigned char* mask,
+                                float* points, void* stream_)
+{
+	if (P < 0 || width <= 0 || (P > 0 && (!depths || !mask || !points))) { set_error_msg("psb_reproject_depth_pinhole: bad argument"); return PSB_ERR_ARG; }
+	if (P == 0) return 0;
+	reproject_depths_kernel<<<cdiv(P, 256), 256, 0, (cudaStream_t)stream_>>>(P, width, fx, fy, cx, cy, depths, mask, points);
+	PSB_LAUNCH_OK();
+	return 0;
+}
+
+int psb_neighbour_depth_pinhole(int N, int width, float fx, float fy, float cx, float cy, float max_pixel_dist, const float* pixels,
+                                const unsigned char* has3D, const float* points_local, const float* colors, float* out_points, float* out_colors,
+                                void* stream_)
+{
+	if (N < 0 || (N > 0 && (!pixels || !has3D || !points_local || !colors || !out_points || !out_colors))) { set_error_msg("psb_neighbour_depth_pinhole: bad argument"); return PSB_ERR_ARG; }
+	if (N == 0) return 0;
+	neighbour_depth_kernel<<<cdiv(N * 32, 256), 256, 0, (cudaStream_t)stream_>>>(N, width, fx, fy, cx, cy, max_pixel_dist, pixels, has3D, points_local,
+	                                                                            colors, out_points, out_colors);
+	PSB_LAUNCH_OK();
+	return 0;
 }
 
 int psb_transform_points(int P, const float* points, const float* transform, float* out_points, void* stream_)

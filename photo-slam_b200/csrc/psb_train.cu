@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(TB, 5) fused_backward_kernel(int first, int P,
 #pragma unroll
 			for (int u = 0; u < PF; u++) {
 				const int i = i0 + u * TB;
-				if (i < n4) { m[u] = gm4[i]; v[u] = gv[i]; }
+				if (i < n4) { m[u] = __ldcs(gm4 + i); v[u] = __ldcs(gv + i); }  // streamed once: do not keep in L2
 			}
 		}
 #pragma unroll
@@ -257,9 +257,9 @@ __global__ void __launch_bounds__(TB, 5) fused_backward_kernel(int first, int P,
 				adam1(p.y, m[u].y, v[u].y, g4.y, lr_rest, ac);
 				adam1(p.z, m[u].z, v[u].z, g4.z, lr_rest, ac);
 				adam1(p.w, m[u].w, v[u].w, g4.w, lr_rest, ac);
-				gp[i] = p; gm4[i] = m[u]; gv[i] = v[u];
+				__stcs(gp + i, p); __stcs(gm4 + i, m[u]); __stcs(gv + i, v[u]);
 			} else {
-				gm4[i] = g4;
+				__stcs(gm4 + i, g4);
 			}
 		}
 	}

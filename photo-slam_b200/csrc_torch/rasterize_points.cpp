@@ -13,6 +13,7 @@
 #include <functional>
 #include <stdexcept>
 #include <tuple>
+#include <vector>
 #include <torch/torch.h>
 #include <torch/library.h>
 #include <c10/cuda/CUDAStream.h>
@@ -122,6 +123,98 @@ torch::Tensor markVisible(torch::Tensor& means3D, torch::Tensor& viewmatrix, tor
 	return present;
 }
 
+// ---- the other torch-typed exports of the reference's libcuda_rasterizer.so / libsimple_knn.so ----
+//   transformPoints, scaleAndTransformThenMarkVisiblePoints   include/operate_points.h:27-40, src/operate_points.cu:73-143
+//   reprojectDepthPinhole, monocularPinholeInactiveGeoDensifyBySearchingNeighborhoodKeypoints
+//                                                              include/stereo_vision.h:26-40, src/stereo_vision.cu:138-215
+//   distCUDA2                                                  third_party/simple-knn/spatial.h:14, spatial.cu:15-26
+void transformPoints(torch::Tensor& points, torch::Tensor& transformmatrix)
+{
+	if (points.ndimension() != 2 || points.size(1) != 3) { AT_ERROR("points must have dimensions (num_points, 3)"); }
+	const int P = points.size(0);
+	torch::Tensor transformed_points = torch::zeros_like(points);
+	if (P != 0) {
+		if (psb_transform_points(P, points.contiguous().data_ptr<float>(), transformmatrix.contiguous().data_ptr<float>(),
+		                         transformed_points.data_ptr<float>(), current_stream()) < 0) { AT_ERROR(psb_last_error()); }
+		points = transformed_points;
+	}
+}
+
+void scaleAndTransformThenMarkVisiblePoints(torch::Tensor& points, torch::Tensor& rots, torch::Tensor& point_not_transformed_mask,
+                                            torch::Tensor& point_unstable_mask, torch::Tensor& transformmatrix, torch::Tensor& viewmatrix,
+                                            torch::Tensor& projmatrix, int& num_transformed, const float scale)
+{
+	if (points.ndimension() != 2 || points.size(1) != 3) { AT_ERROR("points must have dimensions (num_points, 3)"); }
+	torch::Tensor present = markVisible(points, viewmatrix, projmatrix);
+	auto num_points = present.size(0);
+	if (point_not_transformed_mask.size(0) != num_points || point_unstable_mask.size(0) != num_points) { AT_ERROR("points_mask must have dimensions (num_points)"); }
+	torch::Tensor final_mask = torch::logical_and(torch::logical_and(point_not_transformed_mask, point_unstable_mask), present);
+	num_transformed += final_mask.sum().item<int>();
+	const int P = points.size(0);
+	if (P != 0) {
+		torch::Tensor transformed_points = torch::zeros_like(points);
+		torch::Tensor transformed_rots = torch::zeros_like(rots);
+		const auto fm = final_mask.contiguous();
+		if (psb_scale_transform_points(P, scale, points.contiguous().data_ptr<float>(), rots.contiguous().data_ptr<float>(),
+		                               transformmatrix.contiguous().data_ptr<float>(), reinterpret_cast<const unsigned char*>(fm.data_ptr<bool>()),
+		                               transformed_points.data_ptr<float>(), transformed_rots.data_ptr<float>(), /*fix_quaternion_write=*/0,
+		                               current_stream()) < 0) { AT_ERROR(psb_last_error()); }
+		points.index_put_({final_mask}, transformed_points.index({final_mask}));
+		rots.index_put_({final_mask}, transformed_rots.index({final_mask}));
+		point_not_transformed_mask.index_put_({final_mask}, torch::full({P}, false, point_not_transformed_mask.options()).index({final_mask}));
+	}
+}
+
+torch::Tensor reprojectDepthPinhole(torch::Tensor& depth, torch::Tensor& mask, std::vector<float>& intr, int width)
+{
+	if (depth.ndimension() != 1) { AT_ERROR("points must have dimensions (num_points)"); }
+	const int P = depth.size(0);
+	torch::Tensor points;
+	if (P != 0) {
+		points = torch::zeros({P, 3}, depth.options());
+		const auto mk = mask.contiguous();
+		if (psb_reproject_depth_pinhole(P, width, intr[0], intr[1], intr[2], intr[3], depth.contiguous().data_ptr<float>(),
+		                                reinterpret_cast<const unsigned char*>(mk.data_ptr<bool>()), points.data_ptr<float>(), current_stream()) < 0) { AT_ERROR(psb_last_error()); }
+	}
+	return points;
+}
+
+std::tuple<torch::Tensor, torch::Tensor> monocularPinholeInactiveGeoDensifyBySearchingNeighborhoodKeypoints(
+	torch::Tensor& kps_pixel, torch::Tensor& kps_has3D, torch::Tensor& kps_point_local, torch::Tensor& colors, float max_pixel_dist,
+	std::vector<float>& intr, int width)
+{
+	if (kps_pixel.ndimension() != 2 || kps_pixel.size(1) != 2) AT_ERROR("kps_pixel must have dimensions (num_points, 2)");
+	if (kps_has3D.ndimension() != 1) AT_ERROR("kps_has3D must have dimensions (num_points)");
+	if (kps_point_local.ndimension() != 2 || kps_point_local.size(1) != 3) AT_ERROR("kps_point_local must have dimensions (num_points, 3)");
+	const int N = kps_pixel.size(0);
+	torch::Tensor result_pt, result_color;
+	if (N != 0) {
+		result_pt = torch::zeros_like(kps_point_local);
+		result_color = torch::zeros_like(kps_point_local);
+		const auto h3 = kps_has3D.contiguous();
+		if (psb_neighbour_depth_pinhole(N, width, intr[0], intr[1], intr[2], intr[3], max_pixel_dist, kps_pixel.contiguous().data_ptr<float>(),
+		                                reinterpret_cast<const unsigned char*>(h3.data_ptr<bool>()), kps_point_local.contiguous().data_ptr<float>(),
+		                                colors.contiguous().data_ptr<float>(), result_pt.data_ptr<float>(), result_color.data_ptr<float>(),
+		                                current_stream()) < 0) { AT_ERROR(psb_last_error()); }
+		torch::Tensor depth_valid_flags = torch::where(result_pt.index({torch::indexing::Slice(), 2}) > 0.0f, true, false);
+		result_pt = result_pt.index({depth_valid_flags});
+		result_color = result_color.index({depth_valid_flags});
+	}
+	return std::make_tuple(result_pt, result_color);
+}
+
+torch::Tensor distCUDA2(const torch::Tensor& points)
+{
+	const int P = points.size(0);
+	auto float_opts = points.options().dtype(torch::kFloat32);
+	torch::Tensor means = torch::full({P}, 0.0, float_opts);
+	if (P != 0) {
+		const auto pts = points.contiguous();
+		if (psb_dist_cuda2(P, pts.data_ptr<float>(), means.data_ptr<float>(), current_stream()) < 0) { AT_ERROR(psb_last_error()); }
+	}
+	return means;
+}
+
 // ---- B2: the raw-pointer class of cuda_rasterizer/rasterizer.h, same static members, same argument lists ----
 namespace CudaRasterizer {
 class Rasterizer {
@@ -190,6 +283,18 @@ std::tuple<T, T, T, T, T, T, T, T> op_bwd(const T& bg, const T& m3, const T& rad
 	return RasterizeGaussiansBackwardCUDA(bg, m3, radii, col, sc, rot, (float)smod, cov, vm, pm, (float)tfx, (float)tfy, dpix, sh, (int)deg, cp, gb, (int)R, bb, ib);
 }
 T op_vis(T m3, T vm, T pm) { return markVisible(m3, vm, pm); }
+T op_dist(const T& p) { return distCUDA2(p); }
+T op_xform(T p, T m) { transformPoints(p, m); return p; }
+T op_reproject(T d, T mk, double fx, double fy, double cx, double cy, int64_t w)
+{
+	std::vector<float> intr{(float)fx, (float)fy, (float)cx, (float)cy};
+	return reprojectDepthPinhole(d, mk, intr, (int)w);
+}
+std::tuple<T, T> op_neigh(T px, T h3, T pl, T col, double maxd, double fx, double fy, double cx, double cy, int64_t w)
+{
+	std::vector<float> intr{(float)fx, (float)fy, (float)cx, (float)cy};
+	return monocularPinholeInactiveGeoDensifyBySearchingNeighborhoodKeypoints(px, h3, pl, col, (float)maxd, intr, (int)w);
+}
 // B2 through std::function allocators, for the test of the raw-pointer class
 std::tuple<int64_t, T, T> op_b2_fwd(const T& bg, const T& m3, const T& op, const T& sc, const T& rot, const T& vm, const T& pm, double tfx, double tfy,
                                     int64_t H, int64_t W, const T& sh, int64_t deg, const T& cp)
@@ -212,4 +317,8 @@ TORCH_LIBRARY(psb200, m)
 	m.def("rasterize_gaussians_backward", &op_bwd);
 	m.def("mark_visible", &op_vis);
 	m.def("b2_forward", &op_b2_fwd);
+	m.def("dist_cuda2", &op_dist);
+	m.def("transform_points", &op_xform);
+	m.def("reproject_depth_pinhole", &op_reproject);
+	m.def("neighbour_depth_pinhole", &op_neigh);
 }

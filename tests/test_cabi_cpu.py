@@ -78,5 +78,11 @@ def test_libtorch_shim_exports_the_reference_symbols():
                 "_Z30RasterizeGaussiansBackwardCUDARKN2at6TensorES2_S2_S2_S2_S2_fS2_S2_S2_ffS2_S2_iS2_S2_iS2_S2_",
                 "_ZN14CudaRasterizer10Rasterizer11markVisibleEiPfS1_S1_Pb",
                 "_ZN14CudaRasterizer10Rasterizer7forwardESt8functionIFPcmEES4_S4_iiiPKfiiS6_S6_S6_S6_S6_fS6_S6_S6_S6_S6_ffbPfPi",
-                "_ZN14CudaRasterizer10Rasterizer8backwardEiiiiPKfiiS2_S2_S2_S2_fS2_S2_S2_S2_S2_ffPKiPcS5_S5_S2_PfS6_S6_S6_S6_S6_S6_S6_S6_"):
+                "_ZN14CudaRasterizer10Rasterizer8backwardEiiiiPKfiiS2_S2_S2_S2_fS2_S2_S2_S2_S2_ffPKiPcS5_S5_S2_PfS6_S6_S6_S6_S6_S6_S6_S6_",
+                # include/operate_points.h:27-40, include/stereo_vision.h:26-40, third_party/simple-knn/spatial.h:14
+                "_Z15transformPointsRN2at6TensorES1_",
+                "_Z38scaleAndTransformThenMarkVisiblePointsRN2at6TensorES1_S1_S1_S1_S1_S1_Rif",
+                "_Z21reprojectDepthPinholeRN2at6TensorES1_RSt6vectorIfSaIfEEi",
+                "_Z66monocularPinholeInactiveGeoDensifyBySearchingNeighborhoodKeypointsRN2at6TensorES1_S1_S1_fRSt6vectorIfSaIfEEi",
+                "_Z9distCUDA2RKN2at6TensorE"):
         assert sym in out, sym

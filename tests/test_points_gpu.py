@@ -73,3 +73,61 @@ def test_transform_points_and_scale_transform(cuda):
         if fix:  # the corrected write yields the rotation-composed unit quaternion (up to sign)
             q = r_t.cpu().numpy()[mask]
             assert np.all(np.isfinite(q))
+
+
+def test_stereo_vision_kernels_through_the_libtorch_shim(cuda):
+    """reprojectDepthPinhole / monocularPinhole...NeighborhoodKeypoints / distCUDA2 / transformPoints exported by
+    libcuda_rasterizer.so with the reference's C++ signatures, against numpy restatements of
+    reference src/stereo_vision.cu:39-136."""
+    import os
+    from photo_slam_b200 import _lib, points
+    shim = os.path.join(os.path.dirname(_lib.LIB_PATH), "libcuda_rasterizer.so")
+    if not os.path.exists(shim):
+        pytest.skip("libcuda_rasterizer.so not built")
+    torch.ops.load_library(shim)
+    rng = np.random.default_rng(3)
+    W, H = 64, 48
+    fx, fy, cx, cy = 60.0, 61.0, 31.5, 23.5
+    depth = rng.uniform(0.5, 5.0, W * H).astype(np.float32)
+    mask = rng.random(W * H) > 0.4
+    out = torch.ops.psb200.reproject_depth_pinhole(torch.from_numpy(depth).to(cuda), torch.from_numpy(mask).to(cuda), fx, fy, cx, cy, W).cpu().numpy()
+    v, u = np.divmod(np.arange(W * H), W)
+    exp = np.stack([(u - cx) * depth / fx, (v - cy) * depth / fy, depth], 1).astype(np.float32) * mask[:, None]
+    assert np.allclose(out, exp, rtol=1e-6, atol=1e-6)
+
+    N = 700
+    px = np.stack([rng.integers(0, W, N), rng.integers(0, H, N)], 1).astype(np.float32)
+    has3d = rng.random(N) > 0.5
+    pl = rng.uniform(0.5, 4.0, (N, 3)).astype(np.float32)
+    colors = rng.random(W * H * 3 + 8).astype(np.float32)
+    maxd = 40.0
+    rp, rc = torch.ops.psb200.neighbour_depth_pinhole(torch.from_numpy(px).to(cuda), torch.from_numpy(has3d).to(cuda), torch.from_numpy(pl).to(cuda),
+                                                      torch.from_numpy(colors).to(cuda), maxd, fx, fy, cx, cy, W)
+    e_pt, e_col = [], []
+    for i in range(N):
+        pix = int(px[i, 1] * W + px[i, 0])
+        if has3d[i]:
+            p = pl[i]
+        else:
+            best, dep = np.float32(3.4e38), -1.0
+            for j in range(N):
+                if not has3d[j] or j == i:
+                    continue
+                d = np.float32((px[i, 0] - px[j, 0]) ** 2 + (px[i, 1] - px[j, 1]) ** 2)
+                if d > maxd or d >= best:
+                    continue
+                best, dep = d, pl[j, 2]
+            if dep <= 0:
+                continue
+            p = np.array([(int(px[i, 0]) - cx) * dep / fx, (int(px[i, 1]) - cy) * dep / fy, dep], np.float32)
+        if p[2] > 0:
+            e_pt.append(p)
+            e_col.append(colors[pix:pix + 3])
+    assert rp.shape[0] == len(e_pt)
+    assert np.allclose(rp.cpu().numpy(), np.array(e_pt), rtol=1e-5, atol=1e-6) and np.allclose(rc.cpu().numpy(), np.array(e_col))
+
+    pts = torch.randn((5000, 3), device=cuda)
+    assert torch.equal(torch.ops.psb200.dist_cuda2(pts), points.distCUDA2(pts))
+    m = torch.eye(4, device=cuda).flatten().contiguous()
+    m[12:15] = torch.tensor([1.0, 2.0, 3.0], device=cuda)
+    assert torch.allclose(torch.ops.psb200.transform_points(pts.clone(), m), pts + torch.tensor([1.0, 2.0, 3.0], device=cuda))
