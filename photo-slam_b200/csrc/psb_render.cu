@@ -284,7 +284,7 @@ struct BwdSmem {
 };
 
 template <int PPT>
-__global__ void __launch_bounds__(TileGeom<PPT>::THREADS) render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+__global__ void __launch_bounds__(TileGeom<PPT>::THREADS, PPT == 2 ? 6 : 1) render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                                                                             const GaussRec* __restrict__ rec, int W, int H,
                                                                             const float* __restrict__ bg_color, const float* __restrict__ final_Ts,
                                                                             const uint32_t* __restrict__ n_contrib,

@@ -100,6 +100,8 @@ CONFIGS = [
     (3_000, "tum", (64, 48), 9, 0, (0.0, 0.0, 0.0), 12.0),
     # long tile lists (~2500 entries/tile): many staging batches, early termination of saturated tiles
     (150_000, "tum", (320, 240), 11, 3, (0.0, 0.0, 0.0), 2.4),
+    # BASELINE.json's full size (config D): 3 M Gaussians, 1200x680, ~13 M instances — the same bit-exact gates
+    (3_000_000, "replica", None, None, 3, (0.0, 0.0, 0.0), 2.4),
 ]
 
 
