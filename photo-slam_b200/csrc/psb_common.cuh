@@ -142,6 +142,17 @@ __device__ __forceinline__ void tile_rect(float px, float py, int max_radius, in
 	y1 = min(gy, max(0, (int)((py + max_radius + PSB_TILE_Y - 1) / PSB_TILE_Y)));
 }
 
+// Exponent of a splat at offset d = mean - pixel:  power = -0.5 (A dx^2 + C dy^2) - B dx dy.
+// Which products get fused decides the last bit of `power`, hence (rarely) whether alpha passes 1/255 or T passes
+// 1e-4, hence n_contrib. The operation order below is the one the reference's kernels compile to (SASS of reference
+// forward.cu:336 and backward.cu:489: FFMA(dx, A*dx, (C*dy)*dy), then FFMA(sum, -0.5, -((B*dx)*dy))); explicit
+// intrinsics keep it independent of how the surrounding code is unrolled.
+__device__ __forceinline__ float splat_power(float A, float B, float C, float dx, float dy)
+{
+	const float s = __fmaf_rn(dx, __fmul_rn(A, dx), __fmul_rn(dy, __fmul_rn(C, dy)));
+	return __fmaf_rn(s, -0.5f, -__fmul_rn(dy, __fmul_rn(B, dx)));
+}
+
 // ---- async-copy / mbarrier PTX wrappers (TMA 1-D bulk copies) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -95,7 +95,7 @@ template <int PPT>
 __global__ void __launch_bounds__(TileGeom<PPT>::THREADS) render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                                                                             const GaussRec* __restrict__ rec, int W, int H,
                                                                             const float* __restrict__ bg_color, float* __restrict__ out_color,
-                                                                            float* __restrict__ final_T, uint32_t* __restrict__ n_contrib)
+                                                                            float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, int dbg)
 {
 	using G = TileGeom<PPT>;
 	constexpr int NT = G::THREADS;  // = list entries staged per batch (one per thread)
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(TileGeom<PPT>::THREADS) render_fwd_kernel(cons
 
 		const int cnt = min(NT, n - b * NT);
 		bool keep = false;
-		if (tid < cnt) keep = splat_reaches_tile(s_rec[st][tid].q0, s_rec[st][tid].q1, rx0, ry0, rx1, ry1);
+		if (tid < cnt) keep = (dbg & 1) || splat_reaches_tile(s_rec[st][tid].q0, s_rec[st][tid].q1, rx0, ry0, rx1, ry1);
 		const int ccount = compact_block<G::NWARPS>(keep, s_cidx, s_wcnt, tid);
 
 		// Second, per-warp cull: each lane tests one surviving entry against this warp's pixel footprint
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(TileGeom<PPT>::THREADS) render_fwd_kernel(cons
 			bool hit = false;
 			if (kk < ccount) {
 				j = s_cidx[kk];
-				hit = splat_reaches_tile(s_rec[st][j].q0, s_rec[st][j].q1, wx0, wy0, wx1, wy1);
+				hit = (dbg & 2) || splat_reaches_tile(s_rec[st][j].q0, s_rec[st][j].q1, wx0, wy0, wx1, wy1);
 			}
 			uint32_t hits = __ballot_sync(0xffffffffu, hit);
 			while (hits) {
@@ -189,17 +189,17 @@ __global__ void __launch_bounds__(TileGeom<PPT>::THREADS) render_fwd_kernel(cons
 				for (int p = 0; p < PPT; p++) {
 					if (done[p]) continue;
 					const float2 d = make_float2(xy.x - pixfx, xy.y - pixfy[p]);
-					const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+					const float power = splat_power(con_o.x, con_o.y, con_o.z, d.x, d.y);
 					if (power > 0.0f) continue;
-					if (power < q1.z) continue;  // below pmin: alpha < 1/255 for certain, skip exp (see GaussRec)
-					const float alpha = min(0.99f, con_o.w * exp(power));
+					if (power < q1.z && !(dbg & 4)) continue;  // below pmin: alpha < 1/255 for certain, skip exp (see GaussRec)
+					const float alpha = min(0.99f, __fmul_rn(con_o.w, exp(power)));
 					if (alpha < 1.0f / 255.0f) continue;
-					const float test_T = T[p] * (1 - alpha);
+					const float test_T = __fmul_rn(T[p], __fadd_rn(1.f, -alpha));
 					if (test_T < 0.0001f) { done[p] = true; continue; }
 					const float4 q2 = s_rec[st][jj].q2;
-					C[p][0] += q2.x * alpha * T[p];
-					C[p][1] += q2.y * alpha * T[p];
-					C[p][2] += q2.z * alpha * T[p];
+					C[p][0] = __fmaf_rn(T[p], __fmul_rn(q2.x, alpha), C[p][0]);
+					C[p][1] = __fmaf_rn(T[p], __fmul_rn(q2.y, alpha), C[p][1]);
+					C[p][2] = __fmaf_rn(T[p], __fmul_rn(q2.z, alpha), C[p][2]);
 					T[p] = test_T;
 					last_contributor[p] = contributor;
 				}
@@ -401,12 +401,12 @@ __global__ void __launch_bounds__(TileGeom<PPT>::THREADS, PPT == 2 ? 6 : 1) rend
 #pragma unroll
 				for (int p = 0; p < PPT; p++) {
 					d[p] = make_float2(xy.x - pixfx, xy.y - pixfy[p]);
-					const float power = -0.5f * (con_o.x * d[p].x * d[p].x + con_o.z * d[p].y * d[p].y) - con_o.y * d[p].x * d[p].y;
+					const float power = splat_power(con_o.x, con_o.y, con_o.z, d[p].x, d[p].y);
 					active[p] = pos < last_contributor[p] && !(power > 0.0f) && !(power < q1.z);  // q1.z = pmin, see GaussRec
 					G_[p] = 0.f; alpha[p] = 0.f;
 					if (active[p]) {
 						G_[p] = exp(power);
-						alpha[p] = min(0.99f, con_o.w * G_[p]);
+						alpha[p] = min(0.99f, __fmul_rn(con_o.w, G_[p]));
 						active[p] = !(alpha[p] < 1.0f / 255.0f);
 					}
 					any = any || active[p];
@@ -524,10 +524,12 @@ int launch_render_forward(const Camera& cam, const uint2* ranges, const uint32_t
                           float* out_color, float* final_T, uint32_t* n_contrib, cudaStream_t stream)
 {
 	static const int ppt = env_ppt("PSB_FWD_PPT", 2);
+	// debug only: PSB_FWD_DEBUG bit0 = no tile-level cull, bit1 = no per-warp cull, bit2 = no pmin pre-test
+	static const int dbg = getenv("PSB_FWD_DEBUG") ? atoi(getenv("PSB_FWD_DEBUG")) : 0;
 	dim3 grid(cam.grid_x, cam.grid_y, 1);
-	if (ppt == 1) render_fwd_kernel<1><<<grid, TileGeom<1>::THREADS, 0, stream>>>(ranges, point_list, rec, cam.W, cam.H, bg, out_color, final_T, n_contrib);
-	else if (ppt == 2) render_fwd_kernel<2><<<grid, TileGeom<2>::THREADS, 0, stream>>>(ranges, point_list, rec, cam.W, cam.H, bg, out_color, final_T, n_contrib);
-	else render_fwd_kernel<4><<<grid, TileGeom<4>::THREADS, 0, stream>>>(ranges, point_list, rec, cam.W, cam.H, bg, out_color, final_T, n_contrib);
+	if (ppt == 1) render_fwd_kernel<1><<<grid, TileGeom<1>::THREADS, 0, stream>>>(ranges, point_list, rec, cam.W, cam.H, bg, out_color, final_T, n_contrib, dbg);
+	else if (ppt == 2) render_fwd_kernel<2><<<grid, TileGeom<2>::THREADS, 0, stream>>>(ranges, point_list, rec, cam.W, cam.H, bg, out_color, final_T, n_contrib, dbg);
+	else render_fwd_kernel<4><<<grid, TileGeom<4>::THREADS, 0, stream>>>(ranges, point_list, rec, cam.W, cam.H, bg, out_color, final_T, n_contrib, dbg);
 	PSB_LAUNCH_OK();
 	return 0;
 }
