@@ -17,6 +17,12 @@
 // Blending semantics (thresholds, order of operations, n_contrib bookkeeping) follow reference
 // cuda_rasterizer/forward.cu:261-374 and backward.cu:399-557.
 #include <cstdlib>
+#ifndef PSB_FWD_MINBLOCKS
+#define PSB_FWD_MINBLOCKS 1
+#endif
+#ifndef PSB_BWD_MINBLOCKS
+#define PSB_BWD_MINBLOCKS 6
+#endif
 #include "psb_common.cuh"
 #include "psb_kernels.h"
 
@@ -92,11 +98,17 @@ struct TileGeom {
 // Forward
 // =================================================================================================
 template <int PPT>
-__global__ void __launch_bounds__(TileGeom<PPT>::THREADS) render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+__global__ void __launch_bounds__(TileGeom<PPT>::THREADS, PPT == 2 ? PSB_FWD_MINBLOCKS : 1) render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                                                                             const GaussRec* __restrict__ rec, int W, int H,
                                                                             const float* __restrict__ bg_color, float* __restrict__ out_color,
-                                                                            float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, int dbg)
+                                                                            float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, int dbg_arg)
 {
+#ifdef PSB_FWD_DEBUG_SWITCHES
+	const int dbg = dbg_arg;  // bit0: no tile-level cull, bit1: no per-warp cull, bit2: no pmin pre-test
+#else
+	constexpr int dbg = 0;
+	(void)dbg_arg;
+#endif
 	using G = TileGeom<PPT>;
 	constexpr int NT = G::THREADS;  // = list entries staged per batch (one per thread)
 	__shared__ __align__(16) GaussRec s_rec[2][NT];
@@ -284,7 +296,7 @@ struct BwdSmem {
 };
 
 template <int PPT>
-__global__ void __launch_bounds__(TileGeom<PPT>::THREADS, PPT == 2 ? 6 : 1) render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+__global__ void __launch_bounds__(TileGeom<PPT>::THREADS, PPT == 2 ? PSB_BWD_MINBLOCKS : 1) render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                                                                             const GaussRec* __restrict__ rec, int W, int H,
                                                                             const float* __restrict__ bg_color, const float* __restrict__ final_Ts,
                                                                             const uint32_t* __restrict__ n_contrib,
