@@ -18,7 +18,7 @@
 // cuda_rasterizer/forward.cu:261-374 and backward.cu:399-557.
 #include <cstdlib>
 #ifndef PSB_FWD_MINBLOCKS
-#define PSB_FWD_MINBLOCKS 1
+#define PSB_FWD_MINBLOCKS 8
 #endif
 #ifndef PSB_BWD_MINBLOCKS
 #define PSB_BWD_MINBLOCKS 6
