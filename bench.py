@@ -187,20 +187,39 @@ def run_psb(args, world, rank, local, dev):
     clocks = clk.summary()
     ms_step = ms_total / args.steps
 
-    # --- e2e: the call a user makes, host buffers in, loss out, every step
-    stage = dict(gt=torch.empty_like(gt_dev), viewmatrix=torch.empty_like(devcam["viewmatrix"]), projmatrix=torch.empty_like(devcam["projmatrix"]),
-                 campos=torch.empty_like(devcam["campos"]))
-    cam2 = dict(devcam, viewmatrix=stage["viewmatrix"], projmatrix=stage["projmatrix"], campos=stage["campos"])
-    barrier(world)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        for k in ("gt", "viewmatrix", "projmatrix", "campos"):
-            stage[k].copy_(host[k], non_blocking=True)
-        tr.trainForOneIteration(cam2, stage["gt"])
-        loss_host = tr.result()[0]          # device -> host read of the step's loss (blocks, like loss.item())
-    e1.record()
-    barrier(world)
+    # --- e2e: the call a user makes (GaussianTrainer.trainHost): pinned HOST buffers in (ground-truth image + camera,
+    #     copied to the device every step inside the timed region), the step's loss read back to the host every step
+    #     (one step late; the last one by flushHost(), still inside the timed region)
+    if world == 1:
+        hostcam = dict(devcam, viewmatrix=host["viewmatrix"], projmatrix=host["projmatrix"], campos=host["campos"])
+        for _ in range(3):
+            tr.trainHost(hostcam, host["gt"])
+        tr.flushHost()
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        losses = []
+        for _ in range(args.steps):
+            losses.append(tr.trainHost(hostcam, host["gt"]))
+        losses.append(tr.flushHost())
+        e1.record()
+        barrier(world)
+        loss_host = losses[-1]
+        assert sum(l is not None for l in losses) == args.steps
+    else:
+        stage = dict(gt=torch.empty_like(gt_dev), viewmatrix=torch.empty_like(devcam["viewmatrix"]), projmatrix=torch.empty_like(devcam["projmatrix"]),
+                     campos=torch.empty_like(devcam["campos"]))
+        cam2 = dict(devcam, viewmatrix=stage["viewmatrix"], projmatrix=stage["projmatrix"], campos=stage["campos"])
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            for k in ("gt", "viewmatrix", "projmatrix", "campos"):
+                stage[k].copy_(host[k], non_blocking=True)
+            tr.trainForOneIteration(cam2, stage["gt"])
+            loss_host = tr.result()[0]          # device -> host read of the step's loss (blocks, like loss.item())
+        e1.record()
+        barrier(world)
     ms_e2e = max_over_ranks(e0.elapsed_time(e1), world, dev) / args.steps
     h2d = sum(host[k].numel() * 4 for k in ("gt", "viewmatrix", "projmatrix", "campos"))
 

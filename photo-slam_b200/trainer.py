@@ -348,6 +348,46 @@ class GaussianTrainer:
         _lib.check(rc, "psb_trainer_result")
         return out[0], out[1], out[2], n.value
 
+    # ------------------------------------------------------------------------------------------------------------
+    # Host-input front end: what the mapper thread does every iteration — `gt_image = original_image_.cuda()`
+    # (gaussian_mapper.cpp:637), train, `loss.item()` (:705) — with the copy of iteration i overlapped with the GPU
+    # work of iteration i-1 and the loss read back one iteration late, so neither the PCIe copy nor the host
+    # round trip of the read-back leaves the GPU idle.
+    # ------------------------------------------------------------------------------------------------------------
+    def trainHost(self, host_cam, host_gt, mask=None):
+        """host_cam: dict(viewmatrix, projmatrix, campos: pinned CPU tensors; tanfovx, tanfovy, W, H); host_gt: pinned
+        [3,H,W] CPU tensor. Enqueues this iteration and returns the loss of the PREVIOUS one (None on the first call).
+        Call flushHost() after the last iteration to collect the last loss."""
+        dev = self.model.device
+        if not hasattr(self, "_hs"):
+            self._copy = torch.cuda.Stream()
+            mk = lambda t: torch.empty(t.shape, dtype=t.dtype, device=dev)
+            self._hs = [dict(gt=mk(host_gt), viewmatrix=mk(host_cam["viewmatrix"]), projmatrix=mk(host_cam["projmatrix"]),
+                             campos=mk(host_cam["campos"]), ev=torch.cuda.Event(), done=torch.cuda.Event()) for _ in range(2)]
+            self._hslot, self._hpending = 0, None
+        slot = self._hs[self._hslot]
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self._copy):
+            self._copy.wait_event(slot["done"])           # the iteration that last used this slot has finished reading it
+            slot["gt"].copy_(host_gt, non_blocking=True)
+            for k in ("viewmatrix", "projmatrix", "campos"):
+                slot[k].copy_(host_cam[k], non_blocking=True)
+            slot["ev"].record(self._copy)
+        prev = self.result()[0] if self._hpending is not None else None   # blocks on iteration i-1 only
+        cam = dict(host_cam, viewmatrix=slot["viewmatrix"], projmatrix=slot["projmatrix"], campos=slot["campos"])
+        main.wait_event(slot["ev"])
+        self.trainForOneIteration(cam, slot["gt"], mask)
+        slot["done"].record(main)
+        self._hpending = self._hslot
+        self._hslot ^= 1
+        return prev
+
+    def flushHost(self):
+        if getattr(self, "_hpending", None) is None:
+            return None
+        self._hpending = None
+        return self.result()[0]
+
     STAGES = ("preprocess", "depth_sort_scan", "binning", "render_fwd", "loss", "render_bwd", "backward_adam")
 
     def set_profiling(self, enable=True):

@@ -241,3 +241,30 @@ def test_densify_prune_insert_mirror(cuda):
     tr = trainer.GaussianTrainer(m)
     tr.trainForOneIteration(c, torch.rand((3, H, W), device=cuda))
     assert math.isfinite(tr.result()[0])
+
+
+def test_host_front_end_matches_device_path(cuda):
+    """GaussianTrainer.trainHost (pinned host inputs, copy overlapped, loss read one step late) == the plain path."""
+    from photo_slam_b200 import trainer
+    P, wh = 20_000, (320, 240)
+    cam, sc, act, g, c = scene_tensors(P, "tum", seed=6, pose_seed=7, dev=cuda, wh=wh, scale_px=4.0)
+    a = trainer.GaussianModel.from_numpy(sc, cuda)
+    b = trainer.GaussianModel.from_numpy(sc, cuda)
+    for m in (a, b):
+        m.trainingSetup(trainer.GaussianOptimizationParams())
+    ta, tb = trainer.GaussianTrainer(a), trainer.GaussianTrainer(b)
+    gts = [torch.rand((3, wh[1], wh[0])).pin_memory() for _ in range(3)]
+    hostcam = dict(c, viewmatrix=c["viewmatrix"].cpu().pin_memory(), projmatrix=c["projmatrix"].cpu().pin_memory(),
+                   campos=c["campos"].cpu().pin_memory())
+    la, lb = [], []
+    for it in range(6):
+        la.append(ta.trainHost(hostcam, gts[it % 3]))
+        tb.trainForOneIteration(c, gts[it % 3].to(cuda))
+        lb.append(tb.result()[0])
+    la.append(ta.flushHost())
+    assert la[0] is None and len(la) == 7
+    for x, y in zip(la[1:], lb):
+        assert abs(x - y) <= 2e-5 * max(1.0, abs(y)), (x, y)
+    for x, y, lrate in zip(a.tensors(), b.tensors(), LRS):
+        assert ((x - y).abs() > 0.5 * lrate).float().mean().item() < 2e-3
+    assert ta.flushHost() is None
