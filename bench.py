@@ -172,6 +172,14 @@ def run_psb(args, world, rank, local, dev):
         tr.trainForOneIteration(devcam, gt_dev, radii=radii)
         loss0, _, _, n_inst = tr.result()
     P_vis = int((radii > 0).sum().item())
+    # The model trains, so the splat workload drifts from iteration to iteration: every leg below (value, e2e, stage profile)
+    # restarts from this snapshot and therefore times the SAME K iterations.
+    snap, it0 = model.snapshot(), tr.iteration
+
+    def rewind():
+        model.restore(snap)
+        tr.iteration = it0
+        torch.cuda.synchronize()
 
     # --- value: K iterations, inputs resident in HBM, no host sync inside (parameters + moments = 2.1 GB >> L2)
     barrier(world)
@@ -189,27 +197,30 @@ def run_psb(args, world, rank, local, dev):
 
     # --- e2e: the call a user makes (GaussianTrainer.trainHost): pinned HOST buffers in (ground-truth image + camera,
     #     copied to the device every step inside the timed region), the step's loss read back to the host every step
-    #     (one step late; the last one by flushHost(), still inside the timed region)
+    #     (through the trainer's early read-back event); flushHost() drains the last backward inside the timed region
     if world == 1:
         hostcam = dict(devcam, viewmatrix=host["viewmatrix"], projmatrix=host["projmatrix"], campos=host["campos"])
+        rewind()
         for _ in range(3):
             tr.trainHost(hostcam, host["gt"])
         tr.flushHost()
+        rewind()
         barrier(world)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         losses = []
         for _ in range(args.steps):
             losses.append(tr.trainHost(hostcam, host["gt"]))
-        losses.append(tr.flushHost())
+        tr.flushHost()
         e1.record()
         barrier(world)
         loss_host = losses[-1]
-        assert sum(l is not None for l in losses) == args.steps
+        assert len(losses) == args.steps and all(l is not None for l in losses)
     else:
         stage = dict(gt=torch.empty_like(gt_dev), viewmatrix=torch.empty_like(devcam["viewmatrix"]), projmatrix=torch.empty_like(devcam["projmatrix"]),
                      campos=torch.empty_like(devcam["campos"]))
         cam2 = dict(devcam, viewmatrix=stage["viewmatrix"], projmatrix=stage["projmatrix"], campos=stage["campos"])
+        rewind()
         barrier(world)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -224,6 +235,7 @@ def run_psb(args, world, rank, local, dev):
     h2d = sum(host[k].numel() * 4 for k in ("gt", "viewmatrix", "projmatrix", "campos"))
 
     # --- forward-only render throughput and per-stage roofline (separate, untimed-for-value passes)
+    rewind()
     img = torch.empty((3, H, W), device=dev)
     for _ in range(3):
         tr.render(devcam, img)
@@ -239,13 +251,13 @@ def run_psb(args, world, rank, local, dev):
     if world == 1:
         tr.set_profiling(True)
         acc = {}
-        for _ in range(5):
+        for _ in range(args.steps):                     # the same K iterations once more, one CUDA event per stage boundary
             tr.trainForOneIteration(devcam, gt_dev)
             tr.result()
             for k, v in tr.stage_times().items():
                 acc.setdefault(k, []).append(v)
         tr.set_profiling(False)
-        stages = {k: float(np.median(v)) for k, v in acc.items()}
+        stages = {k: float(np.mean(v)) for k, v in acc.items()}
         T_tiles = ((W + 15) // 16) * ((H + 15) // 16)
         ab = algorithmic_bytes(P, P_vis, n_inst, W, H, T_tiles)
         peak = 6650.0

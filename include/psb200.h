@@ -183,8 +183,11 @@ int psb_trainer_backward_slab(psb_trainer* t, int P, int M, const psb_model* mod
 int psb_adam_flat(size_t n, float* param, float* exp_avg, float* exp_avg_sq, const float* grad, float lr,
                   const psb_step* step, float grad_scale, void* stream);
 
-/* Blocks on `stream` and returns the results of the last step / backward / render:
- * out3 = {loss, l1, ssim} (host, may be NULL), *num_rendered (may be NULL).
+/* Returns the results of the last step / backward / render: out3 = {loss, l1, ssim} (host, may be NULL),
+ * *num_rendered (may be NULL). Blocks only until those scalars have reached pinned host memory (an event recorded
+ * right behind the loss kernel), NOT until the step has finished: the caller can read the loss of iteration i and
+ * enqueue iteration i+1 while the backward half of i is still running. Use a stream/device synchronize to wait for
+ * the step itself.
  * Returns PSB_ERR_RETRY when the binning arena was too small for that view: the step was a no-op on the
  * model, the arena has been grown, call the step again. */
 int psb_trainer_result(psb_trainer* t, float* out3, int* num_rendered, void* stream);

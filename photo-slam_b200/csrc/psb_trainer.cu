@@ -21,6 +21,7 @@ struct psb_trainer {
 	double* sums = nullptr;      // device [2]
 	double* h_sums = nullptr;    // pinned [2]
 	uint32_t* h_count = nullptr; // pinned [1]
+	cudaEvent_t readback = nullptr;  // recorded once the instance count (and the loss sums) of the last call are in pinned memory
 	int last_P = 0, last_W = 0, last_H = 0;
 	float last_lambda = 0.2f;
 	bool have_loss = false;
@@ -75,6 +76,7 @@ int ensure(psb_trainer* t, int P, int W, int H, cudaStream_t stream)
 		if ((rc = dev_alloc(&t->sums, 2))) return rc;
 		PSB_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&t->h_sums), 2 * sizeof(double)));
 		PSB_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&t->h_count), sizeof(uint32_t)));
+		PSB_CUDA_OK(cudaEventCreateWithFlags(&t->readback, cudaEventDisableTiming));
 	}
 	const size_t want = (size_t)P * 6 + (1u << 16);
 	if (t->capacity == 0 || (t->capacity < want && t->last_P != P)) {
@@ -153,6 +155,9 @@ int forward_raw(psb_trainer* t, int P, int M, int D, const psb_model* model, con
 	t->mark(2, stream);
 	if ((rc = launch_binning(P, cam, geom, bin, img, geom.counters, t->capacity, stream))) return rc;
 	t->mark(3, stream);
+	// the instance count travels to pinned memory as soon as it exists: psb_trainer_result waits on `readback`, not on the stream
+	PSB_CUDA_OK(cudaMemcpyAsync(t->h_count, geom.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	PSB_CUDA_OK(cudaEventRecord(t->readback, stream));
 	const int res = make_sort_plan(tile_id_bits(cam.grid_x * cam.grid_y)).npass & 1;
 	rc = launch_render_forward(cam, img.ranges, bin.inst[res], geom.rec, background, out_color ? out_color : t->image, img.final_T,
 	                           img.n_contrib, stream);
@@ -172,6 +177,10 @@ int step_impl(psb_trainer* t, int P, int M, const psb_model* model, const psb_ca
 	if ((rc = forward_raw(t, P, M, step->sh_degree, model, camera, background, out_color, radii, geom, bin, img, cam, stream))) return rc;
 	const float* image = out_color ? out_color : t->image;
 	if ((rc = launch_loss(cam.H, cam.W, image, gt_image, mask, step->lambda_dssim, t->dmap, t->sums, t->dL_dpix, stream))) return rc;
+	// loss sums -> pinned memory right behind the loss kernel, so the host can read the loss of this iteration (and start
+	// enqueueing the next one) while the backward half is still running
+	PSB_CUDA_OK(cudaMemcpyAsync(t->h_sums, t->sums, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+	PSB_CUDA_OK(cudaEventRecord(t->readback, stream));
 	t->last_lambda = step->lambda_dssim;
 	t->have_loss = true;
 	t->mark(5, stream);
@@ -218,6 +227,7 @@ int psb_trainer_destroy(psb_trainer* t)
 	cudaFree(t->sink); cudaFree(t->sums);
 	if (t->h_sums) cudaFreeHost(t->h_sums);
 	if (t->h_count) cudaFreeHost(t->h_count);
+	if (t->readback) cudaEventDestroy(t->readback);
 	delete t;
 	return 0;
 }
@@ -302,15 +312,14 @@ int psb_trainer_result(psb_trainer* t, float* out3, int* num_rendered, void* str
 {
 	cudaStream_t stream = (cudaStream_t)stream_;
 	if (!t || t->geom_P < 0) { set_error_msg("psb_trainer_result: no step has run"); return PSB_ERR_ARG; }
-	char* gc = t->geom_chunk;
-	GeomState geom = GeomState::from_chunk(gc, (size_t)t->geom_P);
-	PSB_CUDA_OK(cudaMemcpyAsync(t->h_count, geom.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-	if (t->have_loss) PSB_CUDA_OK(cudaMemcpyAsync(t->h_sums, t->sums, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
-	PSB_CUDA_OK(cudaStreamSynchronize(stream));
+	PSB_CUDA_OK(cudaEventSynchronize(t->readback));
 	const uint32_t n = t->geom_P > 0 ? *t->h_count : 0;
 	if (num_rendered) *num_rendered = (int)n;
 	if (n > t->capacity) {
-		// grow the binning arena; the step that just ran did not touch the parameters
+		// grow the binning arena; the step that just ran did not touch the parameters (its remaining kernels are no-ops,
+		// but they may still be in flight: drain the stream before the arena is replaced)
+		PSB_CUDA_OK(cudaStreamSynchronize(stream));
+		PSB_CUDA_OK(cudaDeviceSynchronize());
 		t->capacity = (size_t)(n * 1.25) + (1u << 16);
 		t->bin_bytes = required_bytes<BinState>(t->capacity);
 		int rc;

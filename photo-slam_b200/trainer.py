@@ -121,6 +121,21 @@ class GaussianModel:
         self.lr_delay_mult_ = args.position_lr_delay_mult
         self.max_steps_ = args.position_lr_max_steps
 
+    # --- training-state snapshot (parameters, Adam moments, densification statistics, step counter); restore copies in
+    #     place so device pointers held elsewhere stay valid. Used by bench.py to time every leg on the same iterations.
+    def snapshot(self):
+        c = lambda ts: [t.clone() for t in ts]
+        return dict(p=c(self.tensors()), m=c(self.exp_avg_), v=c(self.exp_avg_sq_),
+                    stats=c([self.xyz_gradient_accum_, self.denom_, self.max_radii2D_]), step=self.step_, lr=list(self.lr_),
+                    sh=self.active_sh_degree_)
+
+    def restore(self, snap):
+        assert snap["p"][0].shape == self.xyz_.shape, "restore: the model was resized since the snapshot"
+        for dst, src in zip(self.tensors() + self.exp_avg_ + self.exp_avg_sq_ + [self.xyz_gradient_accum_, self.denom_, self.max_radii2D_],
+                            snap["p"] + snap["m"] + snap["v"] + snap["stats"]):
+            dst.copy_(src)
+        self.step_, self.lr_, self.active_sh_degree_ = snap["step"], list(snap["lr"]), snap["sh"]
+
     def exponLrFunc(self, step):
         if step < 0 or (self.lr_init_ == 0.0 and self.lr_final_ == 0.0):
             return 0.0
@@ -350,21 +365,21 @@ class GaussianTrainer:
 
     # ------------------------------------------------------------------------------------------------------------
     # Host-input front end: what the mapper thread does every iteration — `gt_image = original_image_.cuda()`
-    # (gaussian_mapper.cpp:637), train, `loss.item()` (:705) — with the copy of iteration i overlapped with the GPU
-    # work of iteration i-1 and the loss read back one iteration late, so neither the PCIe copy nor the host
-    # round trip of the read-back leaves the GPU idle.
+    # (gaussian_mapper.cpp:637), train, `loss.item()` (:705). The copy of iteration i runs on a side stream while the
+    # GPU still works on iteration i-1, and the loss comes back through psb_trainer_result's early read-back event
+    # (recorded right behind the loss kernel), so the host enqueues iteration i+1 under the backward half of i.
     # ------------------------------------------------------------------------------------------------------------
     def trainHost(self, host_cam, host_gt, mask=None):
         """host_cam: dict(viewmatrix, projmatrix, campos: pinned CPU tensors; tanfovx, tanfovy, W, H); host_gt: pinned
-        [3,H,W] CPU tensor. Enqueues this iteration and returns the loss of the PREVIOUS one (None on the first call).
-        Call flushHost() after the last iteration to collect the last loss."""
+        [3,H,W] CPU tensor. Enqueues this iteration and returns its loss (the GPU may still be in its backward half;
+        flushHost() waits for it)."""
         dev = self.model.device
         if not hasattr(self, "_hs"):
             self._copy = torch.cuda.Stream()
             mk = lambda t: torch.empty(t.shape, dtype=t.dtype, device=dev)
             self._hs = [dict(gt=mk(host_gt), viewmatrix=mk(host_cam["viewmatrix"]), projmatrix=mk(host_cam["projmatrix"]),
                              campos=mk(host_cam["campos"]), ev=torch.cuda.Event(), done=torch.cuda.Event()) for _ in range(2)]
-            self._hslot, self._hpending = 0, None
+            self._hslot = 0
         slot = self._hs[self._hslot]
         main = torch.cuda.current_stream()
         with torch.cuda.stream(self._copy):
@@ -373,20 +388,17 @@ class GaussianTrainer:
             for k in ("viewmatrix", "projmatrix", "campos"):
                 slot[k].copy_(host_cam[k], non_blocking=True)
             slot["ev"].record(self._copy)
-        prev = self.result()[0] if self._hpending is not None else None   # blocks on iteration i-1 only
         cam = dict(host_cam, viewmatrix=slot["viewmatrix"], projmatrix=slot["projmatrix"], campos=slot["campos"])
         main.wait_event(slot["ev"])
         self.trainForOneIteration(cam, slot["gt"], mask)
+        loss = self.result()[0]                           # waits for the loss scalars only (repeats the step on RETRY)
         slot["done"].record(main)
-        self._hpending = self._hslot
         self._hslot ^= 1
-        return prev
+        return loss
 
     def flushHost(self):
-        if getattr(self, "_hpending", None) is None:
-            return None
-        self._hpending = None
-        return self.result()[0]
+        """Waits until every enqueued iteration has finished on the device."""
+        torch.cuda.current_stream().synchronize()
 
     STAGES = ("preprocess", "depth_sort_scan", "binning", "render_fwd", "loss", "render_bwd", "backward_adam")
 
