@@ -1,6 +1,13 @@
 // Trainer step kernels: the per-Gaussian backward fused with the activations' backward, the Adam update of
-// all 59 parameters of the Gaussian and the densification statistics — one kernel per iteration, one read
-// and one write of every parameter / moment, no gradient tensor in memory.
+// all 59 parameters of the Gaussian and the densification statistics — one read and one write of every
+// parameter / moment, no gradient tensor in memory. Two launches per iteration:
+//
+//   gaussian_backward_kernel  one thread per Gaussian: screen-space sums -> gradients of the 14 small parameters
+//                             + their Adam update + densification statistics + the 18-float SH gradient "seed"
+//                             (latency-bound: every global load is issued at the top of the kernel, the f_rest
+//                             parameter rows it has to read arrive by one TMA bulk copy per block);
+//   frest_stream_kernel       Adam over the [P,15,3] SH rows (76 % of the parameter bytes), one float4 per thread,
+//                             gradient = seed products; runs at the HBM copy rate.
 //
 // Replaces, per iteration of reference GaussianMapper::trainForOneIteration (src/gaussian_mapper.cpp:614-774):
 //   computeCov2DCUDA + preprocessCUDA backward (cuda_rasterizer/backward.cu:144-396),
@@ -8,28 +15,21 @@
 //   9 torch::zeros gradient tensors incl. [P,16,3] (src/rasterize_points.cu:148-157),
 //   max_radii2D / addDensificationStats (gaussian_mapper.cpp:714-719, gaussian_model.cpp:817-831),
 //   torch::optim::Adam::step over 6 parameter groups + zero_grad (gaussian_mapper.cpp:769-772).
-//
-// Data movement: the [P,15,3] SH rows (180 B per Gaussian, 76 % of the parameter bytes) of parameters and both
-// moments are moved global -> shared -> global with 1-D TMA bulk copies (one 23 KB copy per tensor per
-// 128-Gaussian block, perfectly coalesced); each thread then walks its own row in shared memory
-// (row stride 45 words: bank-conflict free).
 #include "psb_backward.cuh"
 #include "psb_train.h"
+#include <cstdlib>
+#include <cstdint>
 
 namespace psb {
 
 namespace {
 
+#ifndef PSB_A_MINBLOCKS
+#define PSB_A_MINBLOCKS 5
+#endif
 constexpr int TB = 128;        // Gaussians per block
 constexpr int REST = 45;       // floats per f_rest row (15 coefficients x 3 channels)
-
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes)
-{
-	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+constexpr int SEED = 20;       // floats per seed row: w_1..w_15 at [0..14], masked dL/dRGB at [16..18]
 
 struct AdamCoef { float beta1, beta2, eps, inv_bc1, inv_bc2_sqrt; };
 
@@ -46,24 +46,22 @@ __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, flo
 	p = p - lr_eff * __fdividef(m, denom);
 }
 
-// ADAM = true : fused update (parameters and moments updated in place).
-// ADAM = false: gradients w.r.t. the RAW parameters are written to `grads` (6 segments, reference tensor shapes)
-//               for the data-parallel path (all-reduce between this kernel and adam_kernel).
+// ADAM = true : fused update (parameters and moments of the 14 small parameters updated in place).
+// ADAM = false: gradients w.r.t. the RAW parameters are written to `grads` (reference tensor shapes) for the
+//               data-parallel path (all-reduce between this kernel and adam_kernel).
 //
-// Block = 128 Gaussians. Phase 1 (one thread per Gaussian): screen-space sums -> gradients of the 14 small
-// parameters (+ their Adam update), densification statistics, and the per-Gaussian SH "seed": the 16 basis
-// weights w_k(dir) and the clamp-masked dL/dRGB, from which every SH gradient is w_k * dL/dRGB[ch].
-// The f_rest parameter rows the SH backward has to READ per Gaussian (view-direction term) arrive by one TMA
-// bulk copy per block. Phase 2 (whole block, element-wise, 128-bit coalesced): Adam over the block's
-// [128 x 45] f_rest chunk, gradient looked up from the seeds in shared memory.
+// Block = 128 Gaussians, one thread each. The SH gradient of coefficient k, channel ch is w_k(dir) * dL/dRGB[ch]
+// (clamp-masked): the thread leaves the 15 weights and the 3 masked colour gradients in `seeds` ([P][SEED] floats) and
+// frest_stream_kernel expands them. The f_rest parameter rows the SH backward has to READ (view-direction term of
+// dL/dxyz) arrive by one TMA bulk copy per block; each thread walks its own row in shared memory (row stride 45 words:
+// bank-conflict free).
 template <bool ADAM>
-__global__ void __launch_bounds__(TB, 5) fused_backward_kernel(int first, int P, TrainTensors t, Camera cam, GeomState geom, float4* __restrict__ sink,
+__global__ void __launch_bounds__(TB, PSB_A_MINBLOCKS) gaussian_backward_kernel(int first, int P, TrainTensors t, Camera cam, GeomState geom, float4* __restrict__ sink,
                                                             StepHyper h, GradSegments grads, DensifyStats st,
-                                                            const uint32_t* __restrict__ counters, uint32_t capacity)
+                                                            const uint32_t* __restrict__ counters, uint32_t capacity, float4* __restrict__ seeds)
 {
 	__shared__ __align__(128) float s_p[TB * REST];  // f_rest parameter rows of this block (TMA destination)
-	__shared__ float s_w[TB][17];                    // SH basis weights per Gaussian (k = 0..15), padded
-	__shared__ float s_g[TB][4];                     // clamp-masked dL/dRGB per Gaussian (0 when not visible)
+	__shared__ __align__(16) float s_w[TB][SEED];    // seed rows of this block (copied out 128-bit coalesced at the end)
 	__shared__ __align__(8) uint64_t s_bar;
 
 	// A binning arena that turned out too small leaves the tile lists incomplete: make the step a no-op
@@ -104,7 +102,21 @@ __global__ void __launch_bounds__(TB, 5) fused_backward_kernel(int first, int P,
 	// screen-space sums, as one batch of independent loads — a single memory round trip instead of a chain
 	float sp_xyz[3] = {0, 0, 1}, sp_dc[3] = {0, 0, 0}, sp_sc[3] = {0, 0, 0}, sp_op = 0.f;
 	float4 sp_rot = make_float4(1, 0, 0, 0);
+	// ... and their moments (consumed last): loaded here as well so their latency hides behind the whole backward
+	float m3[3][3], v3[3][3], mo = 0.f, vo = 0.f;
+	float4 mr = make_float4(0, 0, 0, 0), vr = mr;
+	float st_rad = 0.f, st_acc = 0.f, st_den = 0.f;
 	if (valid) {
+		if (ADAM) {
+			const int tsel[3] = {0, 1, 4};
+#pragma unroll
+			for (int a = 0; a < 3; a++)
+#pragma unroll
+				for (int c = 0; c < 3; c++) { m3[a][c] = t.m[tsel[a]][3 * idx + c]; v3[a][c] = t.v[tsel[a]][3 * idx + c]; }
+			mo = t.m[3][idx]; vo = t.v[3][idx];
+			mr = reinterpret_cast<const float4*>(t.m[5])[idx]; vr = reinterpret_cast<const float4*>(t.v[5])[idx];
+		}
+		if (st.enabled) { st_rad = st.max_radii2D[idx]; st_acc = st.xyz_gradient_accum[idx]; st_den = st.denom[idx]; }
 		const uint32_t tt = geom.tiles_touched[idx];
 		const float4 s0 = sink[3 * idx], s1 = sink[3 * idx + 1], s2 = sink[3 * idx + 2];
 		const uint32_t meta = __float_as_uint(geom.rec[idx].q2.w);
@@ -144,9 +156,9 @@ __global__ void __launch_bounds__(TB, 5) fused_backward_kernel(int first, int P,
 			g_rot = make_float4((dL_drot.x - q.x * qd) / qn, (dL_drot.y - q.y * qd) / qn, (dL_drot.z - q.z * qd) / qn, (dL_drot.w - q.w * qd) / qn);
 			g_opac = dL_dopacity * sig * (1.0f - sig);
 			if (st.enabled) {
-				st.max_radii2D[idx] = fmaxf(st.max_radii2D[idx], (float)rec_radius(meta));
-				st.xyz_gradient_accum[idx] += sqrtf(dL_dmean2D.x * dL_dmean2D.x + dL_dmean2D.y * dL_dmean2D.y);
-				st.denom[idx] += 1.0f;
+				st.max_radii2D[idx] = fmaxf(st_rad, (float)rec_radius(meta));
+				st.xyz_gradient_accum[idx] = st_acc + sqrtf(dL_dmean2D.x * dL_dmean2D.x + dL_dmean2D.y * dL_dmean2D.y);
+				st.denom[idx] = st_den + 1.0f;
 			}
 		}
 	}
@@ -176,22 +188,13 @@ __global__ void __launch_bounds__(TB, 5) fused_backward_kernel(int first, int P,
 		}
 		const int ncoef = (h.D + 1) * (h.D + 1);
 #pragma unroll
-		for (int k = 0; k < 16; k++) s_w[tid][k] = (k < ncoef) ? w[k] : 0.f;
-		s_g[tid][0] = gm[0]; s_g[tid][1] = gm[1]; s_g[tid][2] = gm[2];
+		for (int k = 1; k < 16; k++) s_w[tid][k - 1] = (k < ncoef) ? w[k] : 0.f;
+		s_w[tid][15] = 0.f; s_w[tid][16] = gm[0]; s_w[tid][17] = gm[1]; s_w[tid][18] = gm[2]; s_w[tid][19] = 0.f;
 	}
 
 	// ---- the 14 small parameters of this Gaussian
 	if (valid) {
 		if (ADAM) {
-			// load every moment first (independent loads, one round trip), then update, then store
-			float m3[3][3], v3[3][3], mo, vo;
-			const int tsel[3] = {0, 1, 4};
-#pragma unroll
-			for (int a = 0; a < 3; a++)
-#pragma unroll
-				for (int c = 0; c < 3; c++) { m3[a][c] = t.m[tsel[a]][3 * idx + c]; v3[a][c] = t.v[tsel[a]][3 * idx + c]; }
-			mo = t.m[3][idx]; vo = t.v[3][idx];
-			float4 mr = reinterpret_cast<const float4*>(t.m[5])[idx], vr = reinterpret_cast<const float4*>(t.v[5])[idx];
 			const float gx[3] = {g_xyz.x, g_xyz.y, g_xyz.z}, gd[3] = {g_dc.x, g_dc.y, g_dc.z}, gs[3] = {g_scale.x, g_scale.y, g_scale.z};
 #pragma unroll
 			for (int c = 0; c < 3; c++) {
@@ -223,54 +226,48 @@ __global__ void __launch_bounds__(TB, 5) fused_backward_kernel(int first, int P,
 	}
 	__syncthreads();
 
-	// ---- phase 2: element-wise over the block's f_rest chunk, 128-bit coalesced
-	const int n_el = rows * REST;
-	const int n4 = n_el / 4;
-	const float lr_rest = h.lr[2] * ac.inv_bc1;
-	float4* __restrict__ gp = reinterpret_cast<float4*>(t.p[2] + goff);
-	float4* __restrict__ gm4 = ADAM ? reinterpret_cast<float4*>(t.m[2] + goff) : reinterpret_cast<float4*>(grads.g[2] + goff);
-	float4* __restrict__ gv = ADAM ? reinterpret_cast<float4*>(t.v[2] + goff) : nullptr;
-	auto grad_of = [&](int e) {
-		const int row = e / REST, c = e - row * REST;
-		const int k = c / 3 + 1, ch = c - (k - 1) * 3;
-		return s_w[row][k] * s_g[row][ch];
-	};
-	constexpr int PF = 4;  // float4 groups in flight per thread and tensor
-	for (int i0 = tid; i0 < n4; i0 += PF * TB) {
-		float4 m[PF], v[PF];
-		if (ADAM) {
+	// seed rows of this block -> global, 128-bit coalesced
+	const float4* src = reinterpret_cast<const float4*>(&s_w[0][0]);
+	float4* dst = seeds + (size_t)base * (SEED / 4);
+	for (int i = tid; i < rows * (SEED / 4); i += TB) dst[i] = src[i];
+}
+
+// Adam over the f_rest rows of Gaussians [first, P) (ADAM) or their gradient written out
+// (!ADAM), one float4 per thread. The gradient of element (row, k, ch) is seed[row][k-1] * seed[row][16+ch].
+template <bool ADAM>
+__global__ void __launch_bounds__(256) frest_stream_kernel(uint32_t e_first, uint32_t e_end, float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                           float* __restrict__ gout, const float* __restrict__ seeds, float lr_eff, AdamCoef ac,
+                                                           const uint32_t* __restrict__ counters, uint32_t capacity)
+{
+	if (counters[0] > capacity) return;  // overflowing step: no-op (see gaussian_backward_kernel)
+	const uint32_t e = e_first + 4u * (blockIdx.x * 256u + threadIdx.x);
+	if (e >= e_end) return;
+	uint32_t row = e / REST;
+	int c = (int)(e - row * REST);
+	const float* sd = seeds + (size_t)row * SEED;
+	float g[4];
 #pragma unroll
-			for (int u = 0; u < PF; u++) {
-				const int i = i0 + u * TB;
-				if (i < n4) { m[u] = __ldcs(gm4 + i); v[u] = __ldcs(gv + i); }  // streamed once: do not keep in L2
-			}
-		}
-#pragma unroll
-		for (int u = 0; u < PF; u++) {
-			const int i = i0 + u * TB;
-			if (i >= n4) break;
-			const int e = 4 * i;
-			const float4 g4 = make_float4(grad_of(e), grad_of(e + 1), grad_of(e + 2), grad_of(e + 3));
-			if (ADAM) {
-				float4 p = reinterpret_cast<const float4*>(s_p)[i];
-				adam1(p.x, m[u].x, v[u].x, g4.x, lr_rest, ac);
-				adam1(p.y, m[u].y, v[u].y, g4.y, lr_rest, ac);
-				adam1(p.z, m[u].z, v[u].z, g4.z, lr_rest, ac);
-				adam1(p.w, m[u].w, v[u].w, g4.w, lr_rest, ac);
-				__stcs(gp + i, p); __stcs(gm4 + i, m[u]); __stcs(gv + i, v[u]);
-			} else {
-				__stcs(gm4 + i, g4);
-			}
-		}
+	for (int j = 0; j < 4; j++) {
+		const int k = c / 3, ch = c - 3 * k;
+		g[j] = sd[k] * sd[16 + ch];
+		if (++c == REST) { c = 0; sd += SEED; }
 	}
-	for (int e = 4 * n4 + tid; e < n_el; e += TB) {  // < 4 trailing elements of the last block
-		const float g = grad_of(e);
+	if (e + 4 <= e_end) {
 		if (ADAM) {
-			float p = s_p[e], m = t.m[2][goff + e], v = t.v[2][goff + e];
-			adam1(p, m, v, g, lr_rest, ac);
-			t.p[2][goff + e] = p; t.m[2][goff + e] = m; t.v[2][goff + e] = v;
+			float4 pp = __ldcs(reinterpret_cast<const float4*>(p + e)), mm = __ldcs(reinterpret_cast<const float4*>(m + e)),
+			       vv = __ldcs(reinterpret_cast<const float4*>(v + e));
+			adam1(pp.x, mm.x, vv.x, g[0], lr_eff, ac);
+			adam1(pp.y, mm.y, vv.y, g[1], lr_eff, ac);
+			adam1(pp.z, mm.z, vv.z, g[2], lr_eff, ac);
+			adam1(pp.w, mm.w, vv.w, g[3], lr_eff, ac);
+			__stcs(reinterpret_cast<float4*>(p + e), pp); __stcs(reinterpret_cast<float4*>(m + e), mm); __stcs(reinterpret_cast<float4*>(v + e), vv);
 		} else {
-			grads.g[2][goff + e] = g;
+			__stcs(reinterpret_cast<float4*>(gout + e), make_float4(g[0], g[1], g[2], g[3]));
+		}
+	} else {  // < 4 trailing elements (P not a multiple of 4)
+		for (uint32_t j = 0; e + j < e_end; j++) {
+			if (ADAM) adam1(p[e + j], m[e + j], v[e + j], g[j], lr_eff, ac);
+			else gout[e + j] = g[j];
 		}
 	}
 }
@@ -300,15 +297,25 @@ __global__ void adam_tail_kernel(size_t start, size_t n, float* p, float* m, flo
 
 size_t fused_backward_smem_bytes(bool) { return 0; }  // static shared memory only
 
-int launch_fused_backward(bool adam, int first, int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, const StepHyper& h,
-                          const GradSegments& grads, const DensifyStats& st, const uint32_t* counters, uint32_t capacity, cudaStream_t stream)
+int launch_fused_backward(bool adam, int first, int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, float* seeds,
+                          const StepHyper& h, const GradSegments& grads, const DensifyStats& st, const uint32_t* counters, uint32_t capacity,
+                          cudaStream_t stream)
 {
 	if (P - first <= 0) return 0;
 	const int grid = cdiv(P - first, TB);
-	if (adam)
-		fused_backward_kernel<true><<<grid, TB, 0, stream>>>(first, P, t, cam, geom, reinterpret_cast<float4*>(sink), h, grads, st, counters, capacity);
-	else
-		fused_backward_kernel<false><<<grid, TB, 0, stream>>>(first, P, t, cam, geom, reinterpret_cast<float4*>(sink), h, grads, st, counters, capacity);
+	float4* sd4 = reinterpret_cast<float4*>(seeds);
+	float4* sink4 = reinterpret_cast<float4*>(sink);
+	if (!seeds) { set_error_msg("launch_fused_backward: seed scratch missing"); return -1; }
+	if ((size_t)P * REST >= (size_t)UINT32_MAX - 8) { set_error_msg("psb_trainer: too many Gaussians for 32-bit element indices"); return -1; }
+	if (adam) gaussian_backward_kernel<true><<<grid, TB, 0, stream>>>(first, P, t, cam, geom, sink4, h, grads, st, counters, capacity, sd4);
+	else gaussian_backward_kernel<false><<<grid, TB, 0, stream>>>(first, P, t, cam, geom, sink4, h, grads, st, counters, capacity, sd4);
+	PSB_LAUNCH_OK();
+	AdamCoef ac;
+	ac.beta1 = h.beta1; ac.beta2 = h.beta2; ac.eps = h.eps; ac.inv_bc1 = h.inv_bc1; ac.inv_bc2_sqrt = 1.0f / h.bc2_sqrt;
+	const uint32_t e0 = (uint32_t)first * REST, e1 = (uint32_t)P * REST;
+	const unsigned gridB = (unsigned)(((size_t)(e1 - e0) + 1023) / 1024);
+	if (adam) frest_stream_kernel<true><<<gridB, 256, 0, stream>>>(e0, e1, t.p[2], t.m[2], t.v[2], nullptr, seeds, h.lr[2] * ac.inv_bc1, ac, counters, capacity);
+	else frest_stream_kernel<false><<<gridB, 256, 0, stream>>>(e0, e1, nullptr, nullptr, nullptr, grads.g[2], seeds, 0.f, ac, counters, capacity);
 	PSB_LAUNCH_OK();
 	return 0;
 }

@@ -31,8 +31,10 @@ struct DensifyStats {
 
 size_t fused_backward_smem_bytes(bool adam);
 // Gaussians [first, P) (first must be a multiple of 128 so f_rest chunks stay 16-byte aligned)
-int launch_fused_backward(bool adam, int first, int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, const StepHyper& h,
-                          const GradSegments& grads, const DensifyStats& st, const uint32_t* counters, uint32_t capacity, cudaStream_t stream);
+// seeds: scratch [P][20] floats (per-Gaussian SH gradient seeds handed from the per-Gaussian kernel to the f_rest stream kernel)
+int launch_fused_backward(bool adam, int first, int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, float* seeds,
+                          const StepHyper& h, const GradSegments& grads, const DensifyStats& st, const uint32_t* counters, uint32_t capacity,
+                          cudaStream_t stream);
 int launch_adam(size_t n, float* p, float* m, float* v, const float* g, float lr, const StepHyper& h, float grad_scale, cudaStream_t stream);
 int launch_loss(int H, int W, const float* img, const float* gt, const float* mask, float lambda_dssim, float* dmap, double* sums,
                 float* dL_dimg, cudaStream_t stream);

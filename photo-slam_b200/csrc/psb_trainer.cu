@@ -17,7 +17,7 @@ struct psb_trainer {
 	char* img_chunk = nullptr; size_t img_bytes = 0; int img_N = -1;
 	char* bin_chunk = nullptr; size_t bin_bytes = 0; size_t capacity = 0;
 	float* image = nullptr; float* dL_dpix = nullptr; float* dmap = nullptr; size_t pix_alloc = 0;
-	float* sink = nullptr; size_t sink_P = 0;
+	float* sink = nullptr; float* seeds = nullptr; size_t sink_P = 0;
 	double* sums = nullptr;      // device [2]
 	double* h_sums = nullptr;    // pinned [2]
 	uint32_t* h_count = nullptr; // pinned [1]
@@ -69,6 +69,7 @@ int ensure(psb_trainer* t, int P, int W, int H, cudaStream_t stream)
 	if (t->sink_P < (size_t)P) {
 		PSB_CUDA_OK(cudaStreamSynchronize(stream));
 		if ((rc = dev_alloc(&t->sink, (size_t)P * 12))) return rc;
+		if ((rc = dev_alloc(&t->seeds, (size_t)P * 20))) return rc;
 		PSB_CUDA_OK(cudaMemsetAsync(t->sink, 0, (size_t)P * 12 * sizeof(float), stream));
 		t->sink_P = (size_t)P;
 	}
@@ -203,7 +204,7 @@ int step_impl(psb_trainer* t, int P, int M, const psb_model* model, const psb_ca
 	st.enabled = (step->update_densify_stats && model->max_radii2D && model->xyz_gradient_accum && model->denom) ? 1 : 0;
 	st.max_radii2D = model->max_radii2D; st.xyz_gradient_accum = model->xyz_gradient_accum; st.denom = model->denom;
 	const StepHyper h = to_hyper(step);
-	rc = launch_fused_backward(grads == nullptr, 0, P, tt, cam, geom, t->sink, h, gs, st, geom.counters, (uint32_t)t->capacity, stream);
+	rc = launch_fused_backward(grads == nullptr, 0, P, tt, cam, geom, t->sink, t->seeds, h, gs, st, geom.counters, (uint32_t)t->capacity, stream);
 	t->mark(7, stream);
 	t->ev_recorded = t->profiling && t->ev_ready;
 	return rc;
@@ -224,7 +225,7 @@ int psb_trainer_destroy(psb_trainer* t)
 {
 	if (!t) return 0;
 	cudaFree(t->geom_chunk); cudaFree(t->img_chunk); cudaFree(t->bin_chunk); cudaFree(t->image); cudaFree(t->dL_dpix); cudaFree(t->dmap);
-	cudaFree(t->sink); cudaFree(t->sums);
+	cudaFree(t->sink); cudaFree(t->seeds); cudaFree(t->sums);
 	if (t->h_sums) cudaFreeHost(t->h_sums);
 	if (t->h_count) cudaFreeHost(t->h_count);
 	if (t->readback) cudaEventDestroy(t->readback);
@@ -283,7 +284,7 @@ int psb_trainer_backward_slab(psb_trainer* t, int P, int M, const psb_model* mod
 	st.enabled = (step->update_densify_stats && model->max_radii2D && model->xyz_gradient_accum && model->denom) ? 1 : 0;
 	st.max_radii2D = model->max_radii2D; st.xyz_gradient_accum = model->xyz_gradient_accum; st.denom = model->denom;
 	const StepHyper h = to_hyper(step);
-	return launch_fused_backward(false, first, first + count, tt, cam, geom, t->sink, h, gs, st, geom.counters, (uint32_t)t->capacity, (cudaStream_t)stream_);
+	return launch_fused_backward(false, first, first + count, tt, cam, geom, t->sink, t->seeds, h, gs, st, geom.counters, (uint32_t)t->capacity, (cudaStream_t)stream_);
 }
 
 int psb_adam_update(int P, int M, const psb_model* model, float* const* grads, const psb_step* step, float grad_scale, void* stream_)
