@@ -25,90 +25,138 @@ namespace psb {
 // logits, SH split into dc/rest); the activations of reference gaussian_model.cpp:48-71 are applied
 // here instead of by five separate elementwise kernels and a 192 B/Gaussian concatenation.
 // ------------------------------------------------------------------------------------------------
+constexpr int PRE_TB = 128;  // Gaussians per block
+
 template <bool RAW>
-__global__ void __launch_bounds__(128) preprocess_fwd_kernel(GaussIn in, Camera cam, int* __restrict__ radii_out, GeomState geom)
+__global__ void __launch_bounds__(PRE_TB) preprocess_fwd_kernel(GaussIn in, Camera cam, int* __restrict__ radii_out, GeomState geom)
 {
-	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= in.P) return;
+	// SH rows of this block's Gaussians ([128][45] raw f_rest rows or [128][48] activated rows), one TMA bulk copy per block:
+	// they are consumed last (after both culls), so the copy hides behind the projection / covariance arithmetic and each
+	// thread then walks its own row in shared memory (odd / 48-word row stride: at most 2-way bank conflicts on the 48 case).
+	__shared__ __align__(128) float s_sh[PRE_TB * 48];
+	__shared__ __align__(8) uint64_t s_bar;
 
-	if (radii_out) radii_out[idx] = 0;
-	geom.tiles_touched[idx] = 0;
-	geom.depth_key[0][idx] = 0xFFFFFFFFu;
-
-	const float3 p_orig = make_float3(in.means3D[3 * idx], in.means3D[3 * idx + 1], in.means3D[3 * idx + 2]);
-	const float3 p_view = xform4x3(p_orig, cam.view);
-	if (p_view.z <= 0.2f) return;
-
-	const float4 p_hom = xform4x4(p_orig, cam.proj);
-	const float p_w = 1.0f / (p_hom.w + 0.0000001f);
-	const float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
-
-	float cov3D[6];
-	if (in.cov3D_precomp != nullptr) {
-#pragma unroll
-		for (int i = 0; i < 6; i++) cov3D[i] = in.cov3D_precomp[6 * idx + i];
-	} else {
-		float3 s = make_float3(in.scales[3 * idx], in.scales[3 * idx + 1], in.scales[3 * idx + 2]);
-		float4 q = reinterpret_cast<const float4*>(in.rotations)[idx];
-		if (RAW) {
-			s = make_float3(expf(s.x), expf(s.y), expf(s.z));
-			const float n = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
-			q = make_float4(q.x / n, q.y / n, q.z / n, q.w / n);
+	const int tid = threadIdx.x;
+	const int base = blockIdx.x * PRE_TB;
+	const int idx = base + tid;
+	const int rows = min(PRE_TB, in.P - base);
+	const bool want_sh = in.colors_precomp == nullptr;
+	const int row_floats = RAW ? (in.M - 1) * 3 : in.M * 3;
+	const float* sh_src = RAW ? in.sh_rest : in.shs;
+	// staged only for full-degree storage (M == 16) and 16-byte aligned tensors; otherwise rows are read directly
+	const bool staged = want_sh && in.M == 16 && (reinterpret_cast<uintptr_t>(sh_src) & 15) == 0;
+	if (staged) {
+		const size_t goff = (size_t)base * row_floats;
+		const uint32_t row_bytes = (uint32_t)rows * row_floats * sizeof(float);
+		const uint32_t bulk_bytes = row_bytes & ~15u;
+		if (tid == 0) {
+			mbar_init(&s_bar, 1);
+			mbar_fence_init();
+			mbar_arrive_expect_tx(&s_bar, bulk_bytes);
+			bulk_g2s(s_sh, sh_src + goff, bulk_bytes, &s_bar);
+			for (uint32_t i = bulk_bytes / 4; i < row_bytes / 4; i++) s_sh[i] = sh_src[goff + i];  // < 16 trailing bytes (last block)
 		}
-		cov3d_from_scale_rot(s, in.scale_modifier, q, cov3D);
+		__syncthreads();  // the mbarrier must be initialised before any other thread waits on it
 	}
 
-	Cov2DTerms ct;
-	cov2d_terms(p_orig, cam.focal_x, cam.focal_y, cam.tan_fovx, cam.tan_fovy, cov3D, cam.view, ct);
-	ct.cov(0, 0) += 0.3f;
-	ct.cov(1, 1) += 0.3f;
-	const float3 cov = make_float3(float(ct.cov(0, 0)), float(ct.cov(0, 1)), float(ct.cov(1, 1)));
+	// every small per-Gaussian input is loaded up front (one memory round trip instead of a chain across the culls)
+	bool alive = idx < in.P;
+	float3 p_orig = make_float3(0, 0, 1), s = make_float3(0, 0, 0), dc = make_float3(0, 0, 0);
+	float4 q = make_float4(1, 0, 0, 0);
+	float opacity = 0.f;
+	float cov3D[6] = {0, 0, 0, 0, 0, 0};
+	if (alive) {
+		p_orig = make_float3(in.means3D[3 * idx], in.means3D[3 * idx + 1], in.means3D[3 * idx + 2]);
+		if (in.cov3D_precomp != nullptr) {
+#pragma unroll
+			for (int i = 0; i < 6; i++) cov3D[i] = in.cov3D_precomp[6 * idx + i];
+		} else {
+			s = make_float3(in.scales[3 * idx], in.scales[3 * idx + 1], in.scales[3 * idx + 2]);
+			q = reinterpret_cast<const float4*>(in.rotations)[idx];
+		}
+		opacity = in.opacities[idx];
+		if (RAW) dc = make_float3(in.sh_dc[3 * idx], in.sh_dc[3 * idx + 1], in.sh_dc[3 * idx + 2]);
+		else if (!want_sh) dc = make_float3(in.colors_precomp[3 * idx], in.colors_precomp[3 * idx + 1], in.colors_precomp[3 * idx + 2]);
+		if (radii_out) radii_out[idx] = 0;
+		geom.tiles_touched[idx] = 0;
+		geom.depth_key[0][idx] = 0xFFFFFFFFu;
+	}
 
-	const float det = (cov.x * cov.z - cov.y * cov.y);
-	if (det == 0.0f) return;
-	const float det_inv = 1.f / det;
-	const float3 conic = make_float3(cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv);
+	float3 p_view = make_float3(0, 0, 0), conic = make_float3(0, 0, 0);
+	float2 point_image = make_float2(0, 0);
+	float my_radius = 0.f;
+	int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+	if (alive) {
+		p_view = xform4x3(p_orig, cam.view);
+		alive = p_view.z > 0.2f;
+	}
+	if (alive) {
+		const float4 p_hom = xform4x4(p_orig, cam.proj);
+		const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+		const float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
 
-	const float mid = 0.5f * (cov.x + cov.z);
-	const float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
-	const float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
-	const float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
-	const float2 point_image = make_float2(ndc_to_pix(p_proj.x, cam.W), ndc_to_pix(p_proj.y, cam.H));
-	int x0, y0, x1, y1;
-	tile_rect(point_image.x, point_image.y, (int)my_radius, cam.grid_x, cam.grid_y, x0, y0, x1, y1);
-	if ((x1 - x0) * (y1 - y0) == 0) return;
+		if (in.cov3D_precomp == nullptr) {
+			if (RAW) {
+				s = make_float3(expf(s.x), expf(s.y), expf(s.z));
+				const float n = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+				q = make_float4(q.x / n, q.y / n, q.z / n, q.w / n);
+			}
+			cov3d_from_scale_rot(s, in.scale_modifier, q, cov3D);
+		}
+
+		Cov2DTerms ct;
+		cov2d_terms(p_orig, cam.focal_x, cam.focal_y, cam.tan_fovx, cam.tan_fovy, cov3D, cam.view, ct);
+		ct.cov(0, 0) += 0.3f;
+		ct.cov(1, 1) += 0.3f;
+		const float3 cov = make_float3(float(ct.cov(0, 0)), float(ct.cov(0, 1)), float(ct.cov(1, 1)));
+
+		const float det = (cov.x * cov.z - cov.y * cov.y);
+		alive = det != 0.0f;
+		if (alive) {
+			const float det_inv = 1.f / det;
+			conic = make_float3(cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv);
+
+			const float mid = 0.5f * (cov.x + cov.z);
+			const float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
+			const float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+			my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
+			point_image = make_float2(ndc_to_pix(p_proj.x, cam.W), ndc_to_pix(p_proj.y, cam.H));
+			tile_rect(point_image.x, point_image.y, (int)my_radius, cam.grid_x, cam.grid_y, x0, y0, x1, y1);
+			alive = (x1 - x0) * (y1 - y0) != 0;
+		}
+	}
+
+	if (staged) mbar_wait(&s_bar, 0);  // every thread waits: the block must not retire while the copy is in flight
+	if (staged) __syncthreads();       // (also publishes thread 0's trailing plain stores)
+	if (!alive) return;
 
 	float3 rgb;
 	uint32_t clamp_bits = 0;
-	if (in.colors_precomp != nullptr) {
-		rgb = make_float3(in.colors_precomp[3 * idx], in.colors_precomp[3 * idx + 1], in.colors_precomp[3 * idx + 2]);
+	if (!want_sh) {
+		rgb = dc;
 	} else {
 		const float3 campos = make_float3(cam.campos[0], cam.campos[1], cam.campos[2]);
 		float sh[48];
 		const int ncoef = (in.D + 1) * (in.D + 1);
+		const float* row = staged ? s_sh + tid * row_floats : sh_src + (size_t)idx * row_floats;
 		if (RAW) {
-			sh[0] = in.sh_dc[3 * idx]; sh[1] = in.sh_dc[3 * idx + 1]; sh[2] = in.sh_dc[3 * idx + 2];
-			const float* rest = in.sh_rest + (size_t)idx * (in.M - 1) * 3;
+			sh[0] = dc.x; sh[1] = dc.y; sh[2] = dc.z;
 #pragma unroll
-			for (int k = 3; k < 48; k++) sh[k] = (k < ncoef * 3) ? rest[k - 3] : 0.f;
-		} else {
-			const float* row = in.shs + (size_t)idx * in.M * 3;
-			if (in.sh_vec4) {
+			for (int k = 3; k < 48; k++) sh[k] = (k < ncoef * 3) ? row[k - 3] : 0.f;
+		} else if (staged || in.sh_vec4) {
 #pragma unroll
-				for (int k = 0; k < 12; k++) {
-					float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-					if (k * 4 < ncoef * 3) v = reinterpret_cast<const float4*>(row)[k];
-					sh[4 * k] = v.x; sh[4 * k + 1] = v.y; sh[4 * k + 2] = v.z; sh[4 * k + 3] = v.w;
-				}
-			} else {
-#pragma unroll
-				for (int k = 0; k < 48; k++) sh[k] = (k < ncoef * 3) ? row[k] : 0.f;
+			for (int k = 0; k < 12; k++) {
+				float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+				if (k * 4 < ncoef * 3) v = reinterpret_cast<const float4*>(row)[k];
+				sh[4 * k] = v.x; sh[4 * k + 1] = v.y; sh[4 * k + 2] = v.z; sh[4 * k + 3] = v.w;
 			}
+		} else {
+#pragma unroll
+			for (int k = 0; k < 48; k++) sh[k] = (k < ncoef * 3) ? row[k] : 0.f;
 		}
 		rgb = sh_to_rgb(in.D, p_orig, campos, sh, clamp_bits);
 	}
 
-	float opacity = in.opacities[idx];
 	if (RAW) opacity = 1.0f / (1.0f + expf(-opacity));
 
 	const int radius_i = (int)my_radius;
@@ -287,9 +335,9 @@ __global__ void tile_ranges_kernel(const uint32_t* __restrict__ n_dev, uint32_t 
 int launch_preprocess(const GaussIn& in, const Camera& cam, int* radii_out, const GeomState& geom, bool raw, cudaStream_t stream)
 {
 	if (in.P == 0) return 0;
-	const int grid = cdiv(in.P, 128);
-	if (raw) preprocess_fwd_kernel<true><<<grid, 128, 0, stream>>>(in, cam, radii_out, geom);
-	else preprocess_fwd_kernel<false><<<grid, 128, 0, stream>>>(in, cam, radii_out, geom);
+	const int grid = cdiv(in.P, PRE_TB);
+	if (raw) preprocess_fwd_kernel<true><<<grid, PRE_TB, 0, stream>>>(in, cam, radii_out, geom);
+	else preprocess_fwd_kernel<false><<<grid, PRE_TB, 0, stream>>>(in, cam, radii_out, geom);
 	PSB_LAUNCH_OK();
 	return 0;
 }
