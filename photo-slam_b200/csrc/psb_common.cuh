@@ -153,6 +153,63 @@ __device__ __forceinline__ float splat_power(float A, float B, float C, float dx
 	return __fmaf_rn(s, -0.5f, -__fmul_rn(dy, __fmul_rn(B, dx)));
 }
 
+// Can this splat reach alpha >= 1/255 on any pixel of the pixel rectangle [px0,px1] x [py0,py1]?
+// q(d) = 0.5 (A dx^2 + C dy^2) + B dx dy, d = mean - pixel; a contribution needs q <= ln(255 * opacity) = -(pmin + 1e-3)
+// (GaussRec.q1.z). Returns false only when q exceeds that bound (+ a rounding pad) on the WHOLE rectangle, so dropping
+// the splat for that rectangle never changes a pixel.
+// q is a convex quadratic with its minimum (0) at d = 0. If the box does not contain 0, q(t p) = t^2 q(p) shrinks along
+// the segment from any box point p towards 0, so the box minimum sits on an edge FACING the origin: the edge
+// dx = dxlo when dxlo > 0 (dx = dxhi when dxhi < 0), and the same in y — at most two edges, and on each the 1-D minimum
+// is q at the clamped stationary point (corners included by the clamp).
+__device__ __forceinline__ float splat_q(float A, float B, float C, float dx, float dy)
+{
+	const float s = __fmaf_rn(__fmul_rn(A, dx), dx, __fmul_rn(__fmul_rn(C, dy), dy));
+	return __fmaf_rn(__fmul_rn(B, dx), dy, __fmul_rn(0.5f, s));
+}
+struct TileCull {
+	float mx, my, A, B, C, thr, nbc, nba;
+	bool none, all;  // opacity below 1/255: never; conic not positive definite (numerically): always keep
+	__device__ __forceinline__ TileCull(const float4 q0, const float4 q1)
+	{
+		mx = q0.x; my = q0.y; A = q0.z; B = q0.w; C = q1.x; thr = -q1.z;
+		nbc = __fdividef(-B, C); nba = __fdividef(-B, A);  // approximate: a displaced edge point only raises q in second order
+		none = q1.y < (1.0f / 255.0f);
+		all = !(A > 0.f && C > 0.f && A * C > B * B);
+	}
+	__device__ __forceinline__ bool reaches(float px0, float py0, float px1, float py1) const
+	{
+		if (none) return false;
+		const float dxlo = mx - px1, dxhi = mx - px0, dylo = my - py1, dyhi = my - py0;
+		const bool xin = dxlo <= 0.f && dxhi >= 0.f, yin = dylo <= 0.f && dyhi >= 0.f;
+		if ((xin && yin) || all) return true;  // centre inside: q = 0 reachable
+		const float dxm = fmaxf(fabsf(dxlo), fabsf(dxhi)), dym = fmaxf(fabsf(dylo), fabsf(dyhi));
+		const float pad = __fmaf_rn(1e-5f, splat_q(A, fabsf(B), C, dxm, dym), 1e-4f);
+		float qmin = 3.0e38f;
+		if (!xin) {  // vertical edge facing the centre
+			const float ex = dxlo > 0.f ? dxlo : dxhi;
+			qmin = splat_q(A, B, C, ex, fminf(fmaxf(nbc * ex, dylo), dyhi));
+		}
+		if (!yin) {  // horizontal edge facing the centre
+			const float ey = dylo > 0.f ? dylo : dyhi;
+			qmin = fminf(qmin, splat_q(A, B, C, fminf(fmaxf(nba * ey, dxlo), dxhi), ey));
+		}
+		return !(qmin > thr + pad);
+	}
+	// tile (tx, ty) of a W x H image
+	__device__ __forceinline__ bool hit(int tx, int ty, int W, int H) const
+	{
+		const int x0 = tx * PSB_TILE_X, y0 = ty * PSB_TILE_Y;
+		return reaches((float)x0, (float)y0, (float)(min(x0 + PSB_TILE_X, W) - 1), (float)(min(y0 + PSB_TILE_Y, H) - 1));
+	}
+};
+__device__ __forceinline__ bool splat_reaches_tile(const float4 q0, const float4 q1, float px0, float py0, float px1, float py1)
+{
+	return TileCull(q0, q1).reaches(px0, py0, px1, py1);
+}
+constexpr uint32_t TT_VISIBLE = 0x80000000u;  // tight lists: tiles_touched = exact count | this flag (Gaussian passed the culls)
+constexpr uint32_t TT_COUNT = 0x7FFFFFFFu;
+constexpr int TIGHT_MAX_AREA = 32;             // larger rectangles keep every tile (one 32-bit mask per Gaussian, bounded loop)
+
 // ---- async-copy / mbarrier PTX wrappers (TMA 1-D bulk copies) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

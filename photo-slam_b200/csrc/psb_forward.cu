@@ -28,7 +28,7 @@ namespace psb {
 constexpr int PRE_TB = 128;  // Gaussians per block
 
 template <bool RAW>
-__global__ void __launch_bounds__(PRE_TB) preprocess_fwd_kernel(GaussIn in, Camera cam, int* __restrict__ radii_out, GeomState geom)
+__global__ void __launch_bounds__(PRE_TB) preprocess_fwd_kernel(GaussIn in, Camera cam, int* __restrict__ radii_out, GeomState geom, int tight)
 {
 	// SH rows of this block's Gaussians ([128][45] raw f_rest rows or [128][48] activated rows), one TMA bulk copy per block:
 	// they are consumed last (after both culls), so the copy hides behind the projection / covariance arithmetic and each
@@ -168,7 +168,22 @@ __global__ void __launch_bounds__(PRE_TB) preprocess_fwd_kernel(GaussIn in, Came
 	geom.depth_key[0][idx] = __float_as_uint(p_view.z);
 	if (radii_out) radii_out[idx] = radius_i;
 	geom.rect[idx] = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
-	geom.tiles_touched[idx] = (uint32_t)((y1 - y0) * (x1 - x0));
+	uint32_t count = (uint32_t)((y1 - y0) * (x1 - x0));
+	if (tight) {
+		// Tight instance lists (trainer path): only the tiles of the rectangle on which the splat can reach alpha >= 1/255
+		// get an instance. The blend skips such instances anyway (reference forward.cu:338-339 `alpha < 1/255 -> continue`),
+		// so the image and every gradient are unchanged; the lists the sort and the blend walk shrink by about a third.
+		if ((int)count <= TIGHT_MAX_AREA) {
+			const TileCull cull(r.q0, r.q1);
+			uint32_t mask = 0, bit = 1;
+			for (int ty = y0; ty < y1; ty++)
+				for (int tx = x0; tx < x1; tx++, bit <<= 1) mask |= cull.hit(tx, ty, cam.W, cam.H) ? bit : 0u;
+			geom.tile_mask[idx] = mask;
+			count = (uint32_t)__popc(mask);
+		}
+		count |= TT_VISIBLE;
+	}
+	geom.tiles_touched[idx] = count;
 }
 
 // z > 0.2 visibility test only (reference rasterizer_impl.cu:54-66, auxiliary.h:139-164).
@@ -201,7 +216,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(int P, const
 #pragma unroll
 	for (int i = 0; i < SCAN_ITEMS; i++) {
 		const int j = base + i;
-		v[i] = (j < P) ? tiles_touched[order[j]] : 0u;
+		v[i] = (j < P) ? (tiles_touched[order[j]] & TT_COUNT) : 0u;
 		sum += v[i];
 	}
 	uint32_t inc = sum;
@@ -266,32 +281,46 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(int P, const
 // one Gaussian row-major (y outer, x inner) like reference rasterizer_impl.cu:95-108. Small rectangles
 // are written by the owning lane, large ones cooperatively by the warp.
 // ------------------------------------------------------------------------------------------------
+template <bool TIGHT>
 __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint2* __restrict__ rect,
                                                              const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ offsets,
                                                              uint32_t* __restrict__ tile_key, uint32_t* __restrict__ inst, int grid_x,
-                                                             uint32_t capacity, const uint32_t* __restrict__ n_dev)
+                                                             uint32_t capacity, const uint32_t* __restrict__ n_dev,
+                                                             const uint32_t* __restrict__ tile_mask)
 {
 	if (n_dev && *n_dev > capacity) return;  // arena too small for this view: emit nothing (the step becomes a no-op)
 	const int j = blockIdx.x * blockDim.x + threadIdx.x;
 	const int lane = threadIdx.x & 31;
-	uint32_t g = 0, tt = 0, off = 0, x0 = 0, y0 = 0, w = 1;
+	uint32_t g = 0, tt = 0, off = 0, x0 = 0, y0 = 0, w = 1, mask = 0xffffffffu;
 	if (j < P) {
 		g = order[j];
-		tt = tiles_touched[g];
+		tt = tiles_touched[g] & TT_COUNT;
 		if (tt > 0) {
 			const uint2 r = rect[g];
 			x0 = r.x & 0xFFFFu; y0 = r.x >> 16;
 			w = (r.y & 0xFFFFu) - x0;
 			off = offsets[j];
+			// TIGHT: rectangles of up to 32 tiles carry the mask of the tiles that get an instance (popc(mask) == tt)
+			if (TIGHT && w * ((r.y >> 16) - y0) <= (uint32_t)TIGHT_MAX_AREA) mask = tile_mask[g];
 		}
 	}
 	constexpr uint32_t SMALL = 6;
 	if (tt > 0 && tt <= SMALL) {
-		uint32_t tx = x0, ty = y0;
-		for (uint32_t k = 0; k < tt; k++) {
-			tile_key[off + k] = ty * grid_x + tx;
-			inst[off + k] = g;
-			if (++tx == x0 + w) { tx = x0; ty++; }
+		if (TIGHT) {
+			uint32_t m = mask;
+			for (uint32_t k = 0; k < tt; k++) {
+				const uint32_t a = (uint32_t)__ffs(m) - 1u;
+				m &= m - 1u;
+				tile_key[off + k] = (y0 + a / w) * grid_x + x0 + a % w;
+				inst[off + k] = g;
+			}
+		} else {
+			uint32_t tx = x0, ty = y0;
+			for (uint32_t k = 0; k < tt; k++) {
+				tile_key[off + k] = ty * grid_x + tx;
+				inst[off + k] = g;
+				if (++tx == x0 + w) { tx = x0; ty++; }
+			}
 		}
 	}
 	uint32_t big = __ballot_sync(0xffffffffu, tt > SMALL);
@@ -304,6 +333,15 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32
 		const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src);
 		const uint32_t by0 = __shfl_sync(0xffffffffu, y0, src);
 		const uint32_t bw = __shfl_sync(0xffffffffu, w, src);
+		const uint32_t bmask = __shfl_sync(0xffffffffu, mask, src);
+		if (TIGHT && bmask != 0xffffffffu) {  // masked rectangle (<= 32 tiles): lane k owns tile k
+			if ((bmask >> lane) & 1u) {
+				const uint32_t pos = boff + __popc(bmask & ((1u << lane) - 1u));
+				tile_key[pos] = (by0 + lane / bw) * grid_x + bx0 + lane % bw;
+				inst[pos] = bg;
+			}
+			continue;
+		}
 		for (uint32_t k = lane; k < btt; k += 32) {
 			const uint32_t ty = by0 + k / bw, tx = bx0 + k % bw;
 			tile_key[boff + k] = ty * grid_x + tx;
@@ -332,12 +370,12 @@ __global__ void tile_ranges_kernel(const uint32_t* __restrict__ n_dev, uint32_t 
 // ------------------------------------------------------------------------------------------------
 // Host orchestration
 // ------------------------------------------------------------------------------------------------
-int launch_preprocess(const GaussIn& in, const Camera& cam, int* radii_out, const GeomState& geom, bool raw, cudaStream_t stream)
+int launch_preprocess(const GaussIn& in, const Camera& cam, int* radii_out, const GeomState& geom, bool raw, bool tight, cudaStream_t stream)
 {
 	if (in.P == 0) return 0;
 	const int grid = cdiv(in.P, PRE_TB);
-	if (raw) preprocess_fwd_kernel<true><<<grid, PRE_TB, 0, stream>>>(in, cam, radii_out, geom);
-	else preprocess_fwd_kernel<false><<<grid, PRE_TB, 0, stream>>>(in, cam, radii_out, geom);
+	if (raw) preprocess_fwd_kernel<true><<<grid, PRE_TB, 0, stream>>>(in, cam, radii_out, geom, tight ? 1 : 0);
+	else preprocess_fwd_kernel<false><<<grid, PRE_TB, 0, stream>>>(in, cam, radii_out, geom, tight ? 1 : 0);
 	PSB_LAUNCH_OK();
 	return 0;
 }
@@ -371,13 +409,17 @@ int launch_depth_sort_and_scan(int P, GeomState& geom, cudaStream_t stream)
 // Emit + tile sort + ranges. `capacity` = size the binning chunk was carved for; n_dev (device) holds
 // the true instance count when the host does not know it (arena mode), else pass nullptr and n_host = R.
 int launch_binning(int P, const Camera& cam, const GeomState& geom, BinState& bin, const ImgState& img, const uint32_t* n_dev,
-                   size_t n_host, cudaStream_t stream)
+                   size_t n_host, bool tight, cudaStream_t stream)
 {
 	const int num_tiles = cam.grid_x * cam.grid_y;
 	PSB_CUDA_OK(cudaMemsetAsync(img.ranges, 0, (size_t)num_tiles * sizeof(uint2), stream));
 	if (P == 0 || n_host == 0) return 0;
-	emit_instances_kernel<<<cdiv(P, 256), 256, 0, stream>>>(P, geom.order[0], geom.rect, geom.tiles_touched, geom.offsets, bin.tile_key[0],
-	                                                       bin.inst[0], cam.grid_x, (uint32_t)n_host, n_dev);
+	if (tight)
+		emit_instances_kernel<true><<<cdiv(P, 256), 256, 0, stream>>>(P, geom.order[0], geom.rect, geom.tiles_touched, geom.offsets, bin.tile_key[0],
+		                                                             bin.inst[0], cam.grid_x, (uint32_t)n_host, n_dev, geom.tile_mask);
+	else
+		emit_instances_kernel<false><<<cdiv(P, 256), 256, 0, stream>>>(P, geom.order[0], geom.rect, geom.tiles_touched, geom.offsets, bin.tile_key[0],
+		                                                              bin.inst[0], cam.grid_x, (uint32_t)n_host, n_dev, geom.tile_mask);
 	PSB_LAUNCH_OK();
 	const SortPlan plan = make_sort_plan(tile_id_bits(num_tiles));
 	int rc = radix_sort_pairs(bin.tile_key, bin.inst, false, n_dev, n_host, plan, bin.sort_scratch, bin.sort_scratch_bytes, stream);

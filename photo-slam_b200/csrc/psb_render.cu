@@ -32,35 +32,6 @@ namespace {
 
 constexpr int RB = 256;        // list entries per batch
 
-// Can this splat reach alpha >= 1/255 (and power <= 0 is not required here: keeping more is safe)
-// on any pixel of the tile whose pixel-coordinate rectangle is [px0,px1] x [py0,py1]?
-// q(d) = 0.5 (A dx^2 + C dy^2) + B dx dy, d = mean - pixel; contribution needs q <= ln(255 * opacity).
-// Returns false only when q > threshold (+ rounding pad) on the WHOLE rectangle.
-__device__ __forceinline__ bool splat_reaches_tile(const float4 q0, const float4 q1, float px0, float py0, float px1, float py1)
-{
-	const float mx = q0.x, my = q0.y, A = q0.z, B = q0.w, C = q1.x, opac = q1.y;
-	if (opac < (1.0f / 255.0f)) return false;  // alpha <= opacity < 1/255 on every pixel
-	const float dxlo = mx - px1, dxhi = mx - px0, dylo = my - py1, dyhi = my - py0;
-	if (dxlo <= 0.f && dxhi >= 0.f && dylo <= 0.f && dyhi >= 0.f) return true;  // centre inside: q = 0 reachable
-	const float thr = __logf(255.0f * opac) + 1e-3f;
-	const float dxm = fmaxf(fabsf(dxlo), fabsf(dxhi)), dym = fmaxf(fabsf(dylo), fabsf(dyhi));
-	const float S = 0.5f * (fabsf(A) * dxm * dxm + fabsf(C) * dym * dym) + fabsf(B) * dxm * dym;
-	const float pad = 1e-5f * S + 1e-4f;
-	auto q = [&](float dx, float dy) { return 0.5f * (A * dx * dx + C * dy * dy) + B * dx * dy; };
-	// the minimum of a quadratic over a box that does not contain its stationary point lies on the boundary:
-	// check the 4 corners and the clamped 1-D stationary point of each edge.
-	float qmin = fminf(fminf(q(dxlo, dylo), q(dxhi, dylo)), fminf(q(dxlo, dyhi), q(dxhi, dyhi)));
-	if (C > 0.f) {
-		const float s0 = fminf(fmaxf(-B * dxlo / C, dylo), dyhi), s1 = fminf(fmaxf(-B * dxhi / C, dylo), dyhi);
-		qmin = fminf(qmin, fminf(q(dxlo, s0), q(dxhi, s1)));
-	}
-	if (A > 0.f) {
-		const float s0 = fminf(fmaxf(-B * dylo / A, dxlo), dxhi), s1 = fminf(fmaxf(-B * dyhi / A, dxlo), dxhi);
-		qmin = fminf(qmin, fminf(q(s0, dylo), q(s1, dyhi)));
-	}
-	return !(qmin > thr + pad);
-}
-
 // Ordered compaction of `keep` flags over the block; returns total, writes kept entry ids to s_cidx.
 template <int NWARPS>
 __device__ __forceinline__ int compact_block(bool keep, uint8_t* s_cidx, int* s_wcnt, int tid)

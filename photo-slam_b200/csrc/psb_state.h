@@ -26,7 +26,8 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 struct GeomState {
 	GaussRec* rec;            // [P] packed screen-space record (see psb_common.cuh)
 	uint2* rect;              // [P] tile rectangle {x0 | y0<<16, x1 | y1<<16}
-	uint32_t* tiles_touched;  // [P]
+	uint32_t* tiles_touched;  // [P] instance count (tight lists: | TT_VISIBLE, see psb_common.cuh)
+	uint32_t* tile_mask;      // [P] tight lists: bit k set = tile k (row-major) of the rectangle gets an instance (rectangles <= 32 tiles)
 	uint32_t* depth_key[2];   // [P] float bits of view-space depth (0xFFFFFFFF when culled), ping-pong
 	uint32_t* order[2];       // [P] Gaussian indices, ping-pong; order[0] ends up depth-sorted (4 passes)
 	uint32_t* offsets;        // [P] exclusive scan of tiles_touched in depth-sorted order
@@ -41,6 +42,7 @@ struct GeomState {
 		g.rec = carve<GaussRec>(chunk, P);
 		g.rect = carve<uint2>(chunk, P);
 		g.tiles_touched = carve<uint32_t>(chunk, P);
+		g.tile_mask = carve<uint32_t>(chunk, P);
 		g.depth_key[0] = carve<uint32_t>(chunk, P);
 		g.depth_key[1] = carve<uint32_t>(chunk, P);
 		g.order[0] = carve<uint32_t>(chunk, P);

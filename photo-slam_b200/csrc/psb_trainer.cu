@@ -7,6 +7,7 @@
 // by psb_trainer_result so the caller repeats it).
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include "psb_train.h"
 #include "../../include/psb200.h"
 
@@ -25,6 +26,9 @@ struct psb_trainer {
 	int last_P = 0, last_W = 0, last_H = 0;
 	float last_lambda = 0.2f;
 	bool have_loss = false;
+	// tight instance lists: only the tiles a splat can reach get an instance (see preprocess_fwd_kernel); PSB_TIGHT=0 keeps the
+	// reference's full rectangles (A/B measurements only — images and gradients are the same either way)
+	bool tight = !(getenv("PSB_TIGHT") && atoi(getenv("PSB_TIGHT")) == 0);
 	// optional per-stage timing (CUDA events on the step's stream)
 	bool profiling = false;
 	static constexpr int NSTAGE = 8;
@@ -150,11 +154,11 @@ int forward_raw(psb_trainer* t, int P, int M, int D, const psb_model* model, con
 	char* bc = t->bin_chunk; bin = BinState::from_chunk(bc, t->capacity);
 	const GaussIn in = raw_input(P, D, M, model);
 	t->mark(0, stream);
-	if ((rc = launch_preprocess(in, cam, radii, geom, /*raw=*/true, stream))) return rc;
+	if ((rc = launch_preprocess(in, cam, radii, geom, /*raw=*/true, t->tight, stream))) return rc;
 	t->mark(1, stream);
 	if ((rc = launch_depth_sort_and_scan(P, geom, stream))) return rc;
 	t->mark(2, stream);
-	if ((rc = launch_binning(P, cam, geom, bin, img, geom.counters, t->capacity, stream))) return rc;
+	if ((rc = launch_binning(P, cam, geom, bin, img, geom.counters, t->capacity, t->tight, stream))) return rc;
 	t->mark(3, stream);
 	// the instance count travels to pinned memory as soon as it exists: psb_trainer_result waits on `readback`, not on the stream
 	PSB_CUDA_OK(cudaMemcpyAsync(t->h_count, geom.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
