@@ -22,9 +22,9 @@ def test_scratch_sizes_are_pure_and_monotonic():
     for fn in (L.psb_geometry_bytes, L.psb_binning_bytes, L.psb_image_bytes):
         a, b, c = fn(0), fn(1000), fn(100000)
         assert 0 < a <= b <= c and fn(1000) == b
-    # per-Gaussian state: 48 B record + 8 B rect + 4 B tiles + 2x(4+4) B sort ping-pong + 4 B offsets (+ sort status)
+    # per-Gaussian state: 48 B record + 8 B rect + 4 B tiles + 4 B tile mask + 2x(4+4) B sort ping-pong + 4 B offsets (+ sort status)
     per = (L.psb_geometry_bytes(2_000_000) - L.psb_geometry_bytes(1_000_000)) / 1e6
-    assert 80 <= per <= 84, per
+    assert 84 <= per <= 88, per
 
 
 def test_argument_validation_before_any_cuda_call():
