@@ -50,7 +50,7 @@ __global__ void export_geom_kernel(int P, GeomState geom, float* depths, float* 
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= P) return;
-	const uint32_t tt = geom.tiles_touched[i];
+	const uint32_t tt = geom.tile_info[i].z;
 	GaussRec r;
 	r.q0 = r.q1 = r.q2 = make_float4(0, 0, 0, 0);
 	if (tt) r = geom.rec[i];
@@ -115,7 +115,7 @@ int psb_rasterize_forward(psb_alloc_fn geometry_buffer, void* geometry_user, psb
 	const GaussIn in = make_input(P, D, M, means3D, shs, colors_precomp, opacities, scales, scale_modifier, rotations, cov3D_precomp);
 	int rc;
 	if ((rc = launch_preprocess(in, cam, radii, geom, /*raw=*/false, /*tight=*/false, stream))) return rc;
-	if ((rc = launch_depth_sort_and_scan(P, geom, stream))) return rc;
+	if ((rc = launch_depth_sort_and_scan(P, geom, /*scan=*/true, stream))) return rc;
 
 	uint32_t num_rendered = 0;
 	if (P > 0) {
@@ -127,7 +127,7 @@ int psb_rasterize_forward(psb_alloc_fn geometry_buffer, void* geometry_user, psb
 	char* bin_chunk = binning_buffer(required_bytes<BinState>((size_t)num_rendered), binning_user);
 	if (!bin_chunk) { set_error_msg("psb_rasterize_forward: allocator returned null"); return PSB_ERR_ARG; }
 	BinState bin = BinState::from_chunk(bin_chunk, (size_t)num_rendered);
-	if ((rc = launch_binning(P, cam, geom, bin, img, nullptr, (size_t)num_rendered, /*tight=*/false, stream))) return rc;
+	if ((rc = launch_binning(P, cam, geom, bin, img, (size_t)num_rendered, stream))) return rc;
 
 	const int res = make_sort_plan(tile_id_bits(cam.grid_x * cam.grid_y)).npass & 1;
 	if ((rc = launch_render_forward(cam, img.ranges, bin.inst[res], geom.rec, background, out_color, img.final_T, img.n_contrib, stream))) return rc;

@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(GaussIn in, Camera 
                                                              const float* __restrict__ dL_dcolor, int color_stride, GaussGradOut out)
 {
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= in.P || geom.tiles_touched[idx] == 0) return;
+	if (idx >= in.P || geom.tile_info[idx].z == 0) return;
 
 	const float3 mean = make_float3(in.means3D[3 * idx], in.means3D[3 * idx + 1], in.means3D[3 * idx + 2]);
 	float cov3D[6];

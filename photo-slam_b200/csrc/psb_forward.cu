@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(PRE_TB) preprocess_fwd_kernel(GaussIn in, Came
 		if (RAW) dc = make_float3(in.sh_dc[3 * idx], in.sh_dc[3 * idx + 1], in.sh_dc[3 * idx + 2]);
 		else if (!want_sh) dc = make_float3(in.colors_precomp[3 * idx], in.colors_precomp[3 * idx + 1], in.colors_precomp[3 * idx + 2]);
 		if (radii_out) radii_out[idx] = 0;
-		geom.tiles_touched[idx] = 0;
+		geom.tile_info[idx] = make_uint4(0u, 0u, 0u, 0u);
 		geom.depth_key[0][idx] = 0xFFFFFFFFu;
 	}
 
@@ -167,23 +167,22 @@ __global__ void __launch_bounds__(PRE_TB) preprocess_fwd_kernel(GaussIn in, Came
 	geom.rec[idx] = r;
 	geom.depth_key[0][idx] = __float_as_uint(p_view.z);
 	if (radii_out) radii_out[idx] = radius_i;
-	geom.rect[idx] = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
-	uint32_t count = (uint32_t)((y1 - y0) * (x1 - x0));
+	uint32_t count = (uint32_t)((y1 - y0) * (x1 - x0)), mask = 0xffffffffu;
 	if (tight) {
 		// Tight instance lists (trainer path): only the tiles of the rectangle on which the splat can reach alpha >= 1/255
 		// get an instance. The blend skips such instances anyway (reference forward.cu:338-339 `alpha < 1/255 -> continue`),
 		// so the image and every gradient are unchanged; the lists the sort and the blend walk shrink by about a third.
 		if ((int)count <= TIGHT_MAX_AREA) {
 			const TileCull cull(r.q0, r.q1);
-			uint32_t mask = 0, bit = 1;
+			uint32_t bit = 1;
+			mask = 0;
 			for (int ty = y0; ty < y1; ty++)
 				for (int tx = x0; tx < x1; tx++, bit <<= 1) mask |= cull.hit(tx, ty, cam.W, cam.H) ? bit : 0u;
-			geom.tile_mask[idx] = mask;
 			count = (uint32_t)__popc(mask);
 		}
 		count |= TT_VISIBLE;
 	}
-	geom.tiles_touched[idx] = count;
+	geom.tile_info[idx] = make_uint4((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16), count, mask);
 }
 
 // z > 0.2 visibility test only (reference rasterizer_impl.cu:54-66, auxiliary.h:139-164).
@@ -196,11 +195,45 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
 	present[idx] = pv.z > 0.2f ? 1 : 0;
 }
 
+// Warp-wide decoupled look-back (called by warp 0 of a tile, tiles taken in ticket order): publishes this tile's
+// aggregate, returns the exclusive prefix of the tile, then publishes the inclusive prefix.
+// status word: 2 flag bits (1 = aggregate, 2 = inclusive) | 30-bit value; 32 predecessors per round trip.
+__device__ __forceinline__ uint32_t lookback_exclusive(uint32_t* status, uint32_t tile, uint32_t block_total, int lane)
+{
+	uint32_t excl = 0;
+	volatile uint32_t* st = status;
+	if (tile == 0) {
+		if (lane == 0) st[0] = (2u << 30) | block_total;
+		return 0;
+	}
+	if (lane == 0) st[tile] = (1u << 30) | block_total;
+	int p = (int)tile - 1;
+	while (true) {
+		const int q = p - lane;
+		uint32_t s = (q >= 0) ? st[q] : (2u << 30);
+		// lanes closer to the tile must be published before a farther inclusive value can be used
+		uint32_t unpublished = __ballot_sync(0xffffffffu, (s >> 30) == 0u);
+		uint32_t incl = __ballot_sync(0xffffffffu, (s >> 30) == 2u);
+		const int first_incl = incl ? (__ffs(incl) - 1) : 32;
+		const int first_unpub = unpublished ? (__ffs(unpublished) - 1) : 32;
+		if (first_unpub < first_incl) continue;  // poll again (same window)
+		const int upto = min(first_incl, 31);
+		uint32_t contrib = (lane <= upto) ? (s & ((1u << 30) - 1u)) : 0u;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+		excl += contrib;
+		if (first_incl < 32) break;
+		p -= 32;
+	}
+	if (lane == 0) st[tile] = (2u << 30) | ((excl + block_total) & ((1u << 30) - 1u));
+	return excl;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Single-pass exclusive scan (decoupled look-back) of tiles_touched taken in depth-sorted order.
 // status word: 2 flag bits | 30-bit value. counters[0] <- total (num_rendered).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles_touched,
+__global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(int P, const uint32_t* __restrict__ order, const uint4* __restrict__ tile_info,
                                                                     uint32_t* __restrict__ offsets, uint32_t* __restrict__ counters,
                                                                     uint32_t* __restrict__ status)
 {
@@ -216,7 +249,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(int P, const
 #pragma unroll
 	for (int i = 0; i < SCAN_ITEMS; i++) {
 		const int j = base + i;
-		v[i] = (j < P) ? (tiles_touched[order[j]] & TT_COUNT) : 0u;
+		v[i] = (j < P) ? (tile_info[order[j]].z & TT_COUNT) : 0u;
 		sum += v[i];
 	}
 	uint32_t inc = sum;
@@ -234,33 +267,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(int P, const
 		block_total += s_warp[i];
 	}
 	if (warp == 0) {
-		// warp-wide decoupled look-back: 32 predecessors per round trip
-		uint32_t excl = 0;
-		volatile uint32_t* st = status;
-		if (tile == 0) {
-			if (lane == 0) st[0] = (2u << 30) | block_total;
-		} else {
-			if (lane == 0) st[tile] = (1u << 30) | block_total;
-			int p = (int)tile - 1;
-			while (true) {
-				const int q = p - lane;
-				uint32_t s = (q >= 0) ? st[q] : (2u << 30);
-				// lanes closer to the tile must be published before a farther inclusive value can be used
-				uint32_t unpublished = __ballot_sync(0xffffffffu, (s >> 30) == 0u);
-				uint32_t incl = __ballot_sync(0xffffffffu, (s >> 30) == 2u);
-				const int first_incl = incl ? (__ffs(incl) - 1) : 32;
-				const int first_unpub = unpublished ? (__ffs(unpublished) - 1) : 32;
-				if (first_unpub < first_incl) continue;  // poll again (same window)
-				const int upto = min(first_incl, 31);
-				uint32_t contrib = (lane <= upto) ? (s & ((1u << 30) - 1u)) : 0u;
-#pragma unroll
-				for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-				excl += contrib;
-				if (first_incl < 32) break;
-				p -= 32;
-			}
-			if (lane == 0) st[tile] = (2u << 30) | ((excl + block_total) & ((1u << 30) - 1u));
-		}
+		const uint32_t excl = lookback_exclusive(status, tile, block_total, lane);
 		if (lane == 0) {
 			s_prefix = excl;
 			if ((int)(tile + 1) * SCAN_TILE >= P) counters[0] = excl + block_total;
@@ -281,44 +288,28 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(int P, const
 // one Gaussian row-major (y outer, x inner) like reference rasterizer_impl.cu:95-108. Small rectangles
 // are written by the owning lane, large ones cooperatively by the warp.
 // ------------------------------------------------------------------------------------------------
-template <bool TIGHT>
-__global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint2* __restrict__ rect,
-                                                             const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ offsets,
-                                                             uint32_t* __restrict__ tile_key, uint32_t* __restrict__ inst, int grid_x,
-                                                             uint32_t capacity, const uint32_t* __restrict__ n_dev,
-                                                             const uint32_t* __restrict__ tile_mask)
+// All 32 lanes call with their own Gaussian (tt = 0: nothing to write). TIGHT: rectangles of up to 32 tiles carry the mask
+// of the tiles that get an instance (popc(mask) == tt). put(k, key, g) stores instance k (counted from `off`).
+template <bool TIGHT, typename Put>
+__device__ __forceinline__ void emit_warp(uint32_t g, uint32_t tt, uint32_t off, const uint4 info, int grid_x, int lane, Put put)
 {
-	if (n_dev && *n_dev > capacity) return;  // arena too small for this view: emit nothing (the step becomes a no-op)
-	const int j = blockIdx.x * blockDim.x + threadIdx.x;
-	const int lane = threadIdx.x & 31;
-	uint32_t g = 0, tt = 0, off = 0, x0 = 0, y0 = 0, w = 1, mask = 0xffffffffu;
-	if (j < P) {
-		g = order[j];
-		tt = tiles_touched[g] & TT_COUNT;
-		if (tt > 0) {
-			const uint2 r = rect[g];
-			x0 = r.x & 0xFFFFu; y0 = r.x >> 16;
-			w = (r.y & 0xFFFFu) - x0;
-			off = offsets[j];
-			// TIGHT: rectangles of up to 32 tiles carry the mask of the tiles that get an instance (popc(mask) == tt)
-			if (TIGHT && w * ((r.y >> 16) - y0) <= (uint32_t)TIGHT_MAX_AREA) mask = tile_mask[g];
-		}
-	}
+	const uint32_t x0 = info.x & 0xFFFFu, y0 = info.x >> 16;
+	const uint32_t w = max((info.y & 0xFFFFu) - x0, 1u);
+	const bool masked = TIGHT && tt > 0 && w * ((info.y >> 16) - y0) <= (uint32_t)TIGHT_MAX_AREA;
+	const uint32_t mask = masked ? info.w : 0xffffffffu;
 	constexpr uint32_t SMALL = 6;
 	if (tt > 0 && tt <= SMALL) {
-		if (TIGHT) {
+		if (masked) {
 			uint32_t m = mask;
 			for (uint32_t k = 0; k < tt; k++) {
 				const uint32_t a = (uint32_t)__ffs(m) - 1u;
 				m &= m - 1u;
-				tile_key[off + k] = (y0 + a / w) * grid_x + x0 + a % w;
-				inst[off + k] = g;
+				put(off + k, (y0 + a / w) * grid_x + x0 + a % w, g);
 			}
 		} else {
 			uint32_t tx = x0, ty = y0;
 			for (uint32_t k = 0; k < tt; k++) {
-				tile_key[off + k] = ty * grid_x + tx;
-				inst[off + k] = g;
+				put(off + k, ty * grid_x + tx, g);
 				if (++tx == x0 + w) { tx = x0; ty++; }
 			}
 		}
@@ -334,37 +325,128 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32
 		const uint32_t by0 = __shfl_sync(0xffffffffu, y0, src);
 		const uint32_t bw = __shfl_sync(0xffffffffu, w, src);
 		const uint32_t bmask = __shfl_sync(0xffffffffu, mask, src);
-		if (TIGHT && bmask != 0xffffffffu) {  // masked rectangle (<= 32 tiles): lane k owns tile k
-			if ((bmask >> lane) & 1u) {
-				const uint32_t pos = boff + __popc(bmask & ((1u << lane) - 1u));
-				tile_key[pos] = (by0 + lane / bw) * grid_x + bx0 + lane % bw;
-				inst[pos] = bg;
-			}
+		const bool bmasked = __shfl_sync(0xffffffffu, (int)masked, src) != 0;
+		if (bmasked) {  // masked rectangle (<= 32 tiles): lane k owns tile k
+			if ((bmask >> lane) & 1u) put(boff + __popc(bmask & ((1u << lane) - 1u)), (by0 + lane / bw) * grid_x + bx0 + lane % bw, bg);
 			continue;
 		}
-		for (uint32_t k = lane; k < btt; k += 32) {
-			const uint32_t ty = by0 + k / bw, tx = bx0 + k % bw;
-			tile_key[boff + k] = ty * grid_x + tx;
-			inst[boff + k] = bg;
+		for (uint32_t k = lane; k < btt; k += 32) put(boff + k, (by0 + k / bw) * grid_x + bx0 + k % bw, bg);
+	}
+}
+
+// B1/B2 path: offsets come from scan_offsets_kernel, the instance count is known on the host (capacity = num_rendered).
+__global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint4* __restrict__ tile_info,
+                                                             const uint32_t* __restrict__ offsets, uint32_t* __restrict__ tile_key,
+                                                             uint32_t* __restrict__ inst, int grid_x, uint32_t capacity)
+{
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t g = 0, tt = 0, off = 0;
+	uint4 info = make_uint4(0u, 0u, 0u, 0u);
+	if (j < P) {
+		g = order[j];
+		info = tile_info[g];
+		tt = info.z & TT_COUNT;
+		off = offsets[j];
+	}
+	emit_warp<false>(g, tt, off, info, grid_x, threadIdx.x & 31, [&](uint32_t pos, uint32_t key, uint32_t gg) {
+		if (pos < capacity) { tile_key[pos] = key; inst[pos] = gg; }
+	});
+}
+
+// Trainer path: exclusive scan of the instance counts in depth order (single pass, decoupled look-back) and emission in
+// ONE kernel — one 16-byte gather per Gaussian, no offsets array. The block's instances are laid out in shared memory at
+// their block-local offsets (which need no look-back: warp 0 resolves the block's global prefix meanwhile) and leave as
+// one contiguous, coalesced run. counters[0] <- total instance count; instances beyond `capacity` are not written (the
+// step then degrades to a no-op, see psb_trainer.cu).
+constexpr int EM_THREADS = 256, EM_ITEMS = 4, EM_TILE = EM_THREADS * EM_ITEMS;
+constexpr int EM_STAGE = 5120;  // instances staged per block (40 KB); a block with more writes to global memory directly
+template <bool TIGHT>
+__global__ void __launch_bounds__(EM_THREADS) emit_scan_kernel(int P, const uint32_t* __restrict__ order, const uint4* __restrict__ tile_info,
+                                                               uint32_t* __restrict__ tile_key, uint32_t* __restrict__ inst, int grid_x,
+                                                               uint32_t capacity, uint32_t* __restrict__ counters, uint32_t* __restrict__ status)
+{
+	__shared__ uint32_t s_key[EM_STAGE], s_ins[EM_STAGE];
+	__shared__ uint32_t s_warp[EM_THREADS / 32];
+	__shared__ uint32_t s_tile, s_prefix;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid == 0) s_tile = atomicAdd(&counters[1], 1u);
+	__syncthreads();
+	const uint32_t tile = s_tile;
+	const int base = (int)tile * EM_TILE + tid * EM_ITEMS;
+	uint32_t g[EM_ITEMS], cnt[EM_ITEMS];
+	uint4 info[EM_ITEMS];
+	if (base + EM_ITEMS <= P) {
+		const uint4 o = *reinterpret_cast<const uint4*>(order + base);
+		g[0] = o.x; g[1] = o.y; g[2] = o.z; g[3] = o.w;
+	} else {
+#pragma unroll
+		for (int i = 0; i < EM_ITEMS; i++) g[i] = (base + i < P) ? order[base + i] : 0u;
+	}
+	uint32_t sum = 0;
+#pragma unroll
+	for (int i = 0; i < EM_ITEMS; i++) {
+		info[i] = (base + i < P) ? tile_info[g[i]] : make_uint4(0u, 0u, 0u, 0u);
+		cnt[i] = info[i].z & TT_COUNT;
+		sum += cnt[i];
+	}
+	uint32_t inc = sum;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+		if (lane >= o) inc += u;
+	}
+	if (lane == 31) s_warp[warp] = inc;
+	__syncthreads();
+	uint32_t wb = 0, block_total = 0;
+#pragma unroll
+	for (int i = 0; i < EM_THREADS / 32; i++) {
+		if (i < warp) wb += s_warp[i];
+		block_total += s_warp[i];
+	}
+	const bool staged = block_total <= (uint32_t)EM_STAGE;
+	if (warp == 0) {  // publish the aggregate right away, resolve the prefix while the other warps lay out their instances
+		const uint32_t excl = lookback_exclusive(status, tile, block_total, lane);
+		if (lane == 0) {
+			s_prefix = excl;
+			if ((int)(tile + 1) * EM_TILE >= P) counters[0] = excl + block_total;
 		}
+	}
+	if (!staged) __syncthreads();  // direct emission needs the global prefix first
+	uint32_t run = (staged ? 0u : s_prefix) + wb + inc - sum;
+#pragma unroll
+	for (int i = 0; i < EM_ITEMS; i++) {
+		if (staged)
+			emit_warp<TIGHT>(g[i], cnt[i], run, info[i], grid_x, lane, [&](uint32_t pos, uint32_t key, uint32_t gg) { s_key[pos] = key; s_ins[pos] = gg; });
+		else
+			emit_warp<TIGHT>(g[i], cnt[i], run, info[i], grid_x, lane, [&](uint32_t pos, uint32_t key, uint32_t gg) {
+				if (pos < capacity) { tile_key[pos] = key; inst[pos] = gg; }
+			});
+		run += cnt[i];
+	}
+	if (!staged) return;
+	__syncthreads();
+	const uint32_t prefix = s_prefix;
+	for (uint32_t k = tid; k < block_total; k += EM_THREADS) {
+		const uint32_t pos = prefix + k;
+		if (pos < capacity) { tile_key[pos] = s_key[k]; inst[pos] = s_ins[k]; }
 	}
 }
 
 // Start/end of every tile in the tile-sorted instance list (semantics of reference
 // rasterizer_impl.cu:116-138; ranges must be zeroed beforehand so untouched tiles read {0,0}).
-__global__ void tile_ranges_kernel(const uint32_t* __restrict__ n_dev, uint32_t n_host, const uint32_t* __restrict__ tile_key_sorted,
-                                   uint2* __restrict__ ranges)
+__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ n_dev, uint32_t n_host, const uint32_t* __restrict__ tile_key_sorted,
+                                                          uint2* __restrict__ ranges)
 {
 	const uint32_t n = n_dev ? (*n_dev > n_host ? 0u : *n_dev) : n_host;
-	const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= n) return;
-	const uint32_t cur = tile_key_sorted[idx];
-	if (idx == 0) ranges[cur].x = 0;
-	else {
-		const uint32_t prev = tile_key_sorted[idx - 1];
-		if (cur != prev) { ranges[prev].y = idx; ranges[cur].x = idx; }
+	for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+		const uint32_t cur = tile_key_sorted[idx];
+		if (idx == 0) ranges[cur].x = 0;
+		else {
+			const uint32_t prev = tile_key_sorted[idx - 1];
+			if (cur != prev) { ranges[prev].y = idx; ranges[cur].x = idx; }
+		}
+		if (idx == n - 1) ranges[cur].y = n;
 	}
-	if (idx == n - 1) ranges[cur].y = n;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -388,44 +470,71 @@ int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t*
 	return 0;
 }
 
-// Depth sort + offsets scan. After this geom.order[0] is the depth-sorted permutation,
-// geom.offsets the instance offsets and geom.counters[0] = num_rendered.
-int launch_depth_sort_and_scan(int P, GeomState& geom, cudaStream_t stream)
+// Depth sort (+ offsets scan when `scan`: the B1/B2 path needs the instance count on the host before it can size the
+// binning buffer; the trainer path scans inside emit_scan_kernel). After this geom.order[0] is the depth-sorted
+// permutation; with `scan`, geom.offsets holds the instance offsets and geom.counters[0] = num_rendered.
+int launch_depth_sort_and_scan(int P, GeomState& geom, bool scan, cudaStream_t stream)
 {
 	if (P == 0) return 0;
 	PSB_CUDA_OK(cudaMemsetAsync(geom.counters, 0, 32 * sizeof(uint32_t), stream));
-	PSB_CUDA_OK(cudaMemsetAsync(geom.scan_status, 0, ((size_t)(P + SCAN_TILE - 1) / SCAN_TILE + 1) * sizeof(uint32_t), stream));
+	PSB_CUDA_OK(cudaMemsetAsync(geom.scan_status, 0, scan_status_words((size_t)P) * sizeof(uint32_t), stream));
 	const SortPlan plan = make_sort_plan(32);
 	int rc = radix_sort_pairs(geom.depth_key, geom.order, /*iota_vals=*/true, nullptr, (size_t)P, plan, geom.sort_scratch,
 	                          geom.sort_scratch_bytes, stream);
 	if (rc) return rc;
 	// 4 passes -> result back in buffer 0
-	scan_offsets_kernel<<<cdiv(P, SCAN_TILE), SCAN_THREADS, 0, stream>>>(P, geom.order[0], geom.tiles_touched, geom.offsets, geom.counters,
-	                                                                    geom.scan_status);
-	PSB_LAUNCH_OK();
+	if (scan) {
+		scan_offsets_kernel<<<cdiv(P, SCAN_TILE), SCAN_THREADS, 0, stream>>>(P, geom.order[0], geom.tile_info, geom.offsets, geom.counters,
+		                                                                    geom.scan_status);
+		PSB_LAUNCH_OK();
+	}
 	return 0;
 }
 
-// Emit + tile sort + ranges. `capacity` = size the binning chunk was carved for; n_dev (device) holds
-// the true instance count when the host does not know it (arena mode), else pass nullptr and n_host = R.
-int launch_binning(int P, const Camera& cam, const GeomState& geom, BinState& bin, const ImgState& img, const uint32_t* n_dev,
-                   size_t n_host, bool tight, cudaStream_t stream)
+static int ranges_grid(size_t n_host)
+{
+	const size_t want = (n_host + 255) / 256;
+	return (int)(want < 148 * 16 ? (want ? want : 1) : 148 * 16);
+}
+
+// B1/B2 path: emit + tile sort + ranges for a known instance count R (= n_host; the binning chunk was carved for it).
+int launch_binning(int P, const Camera& cam, const GeomState& geom, BinState& bin, const ImgState& img, size_t n_host, cudaStream_t stream)
 {
 	const int num_tiles = cam.grid_x * cam.grid_y;
 	PSB_CUDA_OK(cudaMemsetAsync(img.ranges, 0, (size_t)num_tiles * sizeof(uint2), stream));
 	if (P == 0 || n_host == 0) return 0;
-	if (tight)
-		emit_instances_kernel<true><<<cdiv(P, 256), 256, 0, stream>>>(P, geom.order[0], geom.rect, geom.tiles_touched, geom.offsets, bin.tile_key[0],
-		                                                             bin.inst[0], cam.grid_x, (uint32_t)n_host, n_dev, geom.tile_mask);
-	else
-		emit_instances_kernel<false><<<cdiv(P, 256), 256, 0, stream>>>(P, geom.order[0], geom.rect, geom.tiles_touched, geom.offsets, bin.tile_key[0],
-		                                                              bin.inst[0], cam.grid_x, (uint32_t)n_host, n_dev, geom.tile_mask);
+	emit_instances_kernel<<<cdiv(P, 256), 256, 0, stream>>>(P, geom.order[0], geom.tile_info, geom.offsets, bin.tile_key[0], bin.inst[0], cam.grid_x,
+	                                                       (uint32_t)n_host);
 	PSB_LAUNCH_OK();
 	const SortPlan plan = make_sort_plan(tile_id_bits(num_tiles));
-	int rc = radix_sort_pairs(bin.tile_key, bin.inst, false, n_dev, n_host, plan, bin.sort_scratch, bin.sort_scratch_bytes, stream);
+	int rc = radix_sort_pairs(bin.tile_key, bin.inst, false, nullptr, n_host, plan, bin.sort_scratch, bin.sort_scratch_bytes, stream);
 	if (rc) return rc;
 	const int res = plan.npass & 1;
-	tile_ranges_kernel<<<(unsigned)((n_host + 255) / 256), 256, 0, stream>>>(n_dev, (uint32_t)n_host, bin.tile_key[res], img.ranges);
+	tile_ranges_kernel<<<ranges_grid(n_host), 256, 0, stream>>>(nullptr, (uint32_t)n_host, bin.tile_key[res], img.ranges);
+	PSB_LAUNCH_OK();
+	return 0;
+}
+
+// Trainer path: scan + emit in one kernel, tile sort, ranges. The instance count stays on the device
+// (geom.counters[0]); `capacity` = size the binning chunk was carved for.
+int launch_scan_binning(int P, const Camera& cam, const GeomState& geom, BinState& bin, const ImgState& img, size_t capacity, bool tight,
+                        cudaStream_t stream)
+{
+	const int num_tiles = cam.grid_x * cam.grid_y;
+	PSB_CUDA_OK(cudaMemsetAsync(img.ranges, 0, (size_t)num_tiles * sizeof(uint2), stream));
+	if (P == 0 || capacity == 0) return 0;
+	const SortPlan plan = make_sort_plan(tile_id_bits(num_tiles));
+	if (tight)
+		emit_scan_kernel<true><<<cdiv(P, EM_TILE), EM_THREADS, 0, stream>>>(P, geom.order[0], geom.tile_info, bin.tile_key[0], bin.inst[0], cam.grid_x,
+		                                                                  (uint32_t)capacity, geom.counters, geom.scan_status);
+	else
+		emit_scan_kernel<false><<<cdiv(P, EM_TILE), EM_THREADS, 0, stream>>>(P, geom.order[0], geom.tile_info, bin.tile_key[0], bin.inst[0], cam.grid_x,
+		                                                                   (uint32_t)capacity, geom.counters, geom.scan_status);
+	PSB_LAUNCH_OK();
+	int rc = radix_sort_pairs(bin.tile_key, bin.inst, false, geom.counters, capacity, plan, bin.sort_scratch, bin.sort_scratch_bytes, stream);
+	if (rc) return rc;
+	const int res = plan.npass & 1;
+	tile_ranges_kernel<<<ranges_grid(capacity), 256, 0, stream>>>(geom.counters, (uint32_t)capacity, bin.tile_key[res], img.ranges);
 	PSB_LAUNCH_OK();
 	return 0;
 }

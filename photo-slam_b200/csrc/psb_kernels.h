@@ -41,12 +41,13 @@ struct GaussGradOut {
 	float* dL_drots;     // [P,4]
 };
 
-// tight: instance lists hold only the tiles a splat can reach (trainer path; see preprocess_fwd_kernel) — pass the same flag to launch_binning
+// tight: instance lists hold only the tiles a splat can reach (trainer path; see preprocess_fwd_kernel) — pass the same flag to launch_scan_binning
 int launch_preprocess(const GaussIn& in, const Camera& cam, int* radii_out, const GeomState& geom, bool raw, bool tight, cudaStream_t stream);
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t stream);
-int launch_depth_sort_and_scan(int P, GeomState& geom, cudaStream_t stream);
-int launch_binning(int P, const Camera& cam, const GeomState& geom, BinState& bin, const ImgState& img, const uint32_t* n_dev,
-                   size_t n_host, bool tight, cudaStream_t stream);
+int launch_depth_sort_and_scan(int P, GeomState& geom, bool scan, cudaStream_t stream);
+int launch_binning(int P, const Camera& cam, const GeomState& geom, BinState& bin, const ImgState& img, size_t n_host, cudaStream_t stream);
+int launch_scan_binning(int P, const Camera& cam, const GeomState& geom, BinState& bin, const ImgState& img, size_t capacity, bool tight,
+                        cudaStream_t stream);
 int launch_render_forward(const Camera& cam, const uint2* ranges, const uint32_t* point_list, const GaussRec* rec, const float* bg,
                           float* out_color, float* final_T, uint32_t* n_contrib, cudaStream_t stream);
 int launch_render_backward(const Camera& cam, const uint2* ranges, const uint32_t* point_list, const GaussRec* rec, const float* bg,

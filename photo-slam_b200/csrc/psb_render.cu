@@ -316,6 +316,8 @@ __global__ void __launch_bounds__(TileGeom<PPT>::THREADS, PPT == 2 ? PSB_BWD_MIN
 		}
 	}
 
+	const bool has_bg = bg_color[0] != 0.f || bg_color[1] != 0.f || bg_color[2] != 0.f;  // uniform over the grid
+
 	// Nothing behind the deepest last contributor of the tile can receive gradient: start there.
 	const int warp_maxc = __reduce_max_sync(0xffffffffu, my_max);
 	if (lane == 0) sm.wcnt[warp] = warp_maxc;
@@ -418,7 +420,8 @@ __global__ void __launch_bounds__(TileGeom<PPT>::THREADS, PPT == 2 ? PSB_BWD_MIN
 					}
 					dL_dalpha *= T[p];
 					last_alpha[p] = alpha[p];
-					dL_dalpha += (-T_final[p] / (1.f - alpha[p])) * bg_dot_dpixel[p];
+					// background term (reference backward.cu:512-516); with a black background it adds (-x) * 0 = -0: skipped
+					if (has_bg) dL_dalpha += (-T_final[p] / (1.f - alpha[p])) * bg_dot_dpixel[p];
 
 					const float dL_dG = con_o.w * dL_dalpha;
 					const float gdx = G_[p] * d[p].x;

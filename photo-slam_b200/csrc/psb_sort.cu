@@ -272,7 +272,6 @@ int radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], bool iota_vals, const
 	uint32_t* status = tickets + 16;
 	const size_t ntiles = sort_tiles(n_host);
 	PSB_CUDA_OK(cudaMemsetAsync(scratch, 0, need, stream));
-
 	int hgrid = (int)((n_host + 256 * 4 * 8 - 1) / (256 * 4 * 8));
 	if (hgrid > 148 * 8) hgrid = 148 * 8;
 	if (hgrid < 1) hgrid = 1;

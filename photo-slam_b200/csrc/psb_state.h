@@ -21,18 +21,21 @@ static inline T* carve(char*& chunk, size_t count, size_t alignment = 128)
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+// look-back status words for the scan over P Gaussians (sized for the smaller of the two scan tiles: 1024, emit_scan_kernel)
+static inline size_t scan_status_words(size_t P) { return (P + 1023) / 1024 + 1; }
 
 // Per-Gaussian state: function of P.
 struct GeomState {
 	GaussRec* rec;            // [P] packed screen-space record (see psb_common.cuh)
-	uint2* rect;              // [P] tile rectangle {x0 | y0<<16, x1 | y1<<16}
-	uint32_t* tiles_touched;  // [P] instance count (tight lists: | TT_VISIBLE, see psb_common.cuh)
-	uint32_t* tile_mask;      // [P] tight lists: bit k set = tile k (row-major) of the rectangle gets an instance (rectangles <= 32 tiles)
+	// [P] {x0 | y0<<16, x1 | y1<<16, instance count, tile mask}: the tile rectangle, the number of (Gaussian, tile)
+	// instances (0 when culled; tight lists: exact count | TT_VISIBLE) and, for tight lists over rectangles of <= 32 tiles,
+	// bit k set = tile k (row-major) of the rectangle gets an instance. One 16-byte gather per Gaussian in depth order.
+	uint4* tile_info;
 	uint32_t* depth_key[2];   // [P] float bits of view-space depth (0xFFFFFFFF when culled), ping-pong
 	uint32_t* order[2];       // [P] Gaussian indices, ping-pong; order[0] ends up depth-sorted (4 passes)
-	uint32_t* offsets;        // [P] exclusive scan of tiles_touched in depth-sorted order
+	uint32_t* offsets;        // [P] exclusive scan of the instance counts in depth-sorted order (B1/B2 path only)
 	uint32_t* counters;       // [32] counters[0] = num_rendered, [1] = scan ticket
-	uint32_t* scan_status;    // [ceil(P / SCAN_TILE) + 1]
+	uint32_t* scan_status;    // [scan_status_words(P)]
 	char* sort_scratch;       // radix scratch for 4 passes over P
 	size_t sort_scratch_bytes;
 
@@ -40,16 +43,14 @@ struct GeomState {
 	{
 		GeomState g;
 		g.rec = carve<GaussRec>(chunk, P);
-		g.rect = carve<uint2>(chunk, P);
-		g.tiles_touched = carve<uint32_t>(chunk, P);
-		g.tile_mask = carve<uint32_t>(chunk, P);
+		g.tile_info = carve<uint4>(chunk, P);
 		g.depth_key[0] = carve<uint32_t>(chunk, P);
 		g.depth_key[1] = carve<uint32_t>(chunk, P);
 		g.order[0] = carve<uint32_t>(chunk, P);
 		g.order[1] = carve<uint32_t>(chunk, P);
 		g.offsets = carve<uint32_t>(chunk, P);
 		g.counters = carve<uint32_t>(chunk, 32);
-		g.scan_status = carve<uint32_t>(chunk, (P + SCAN_TILE - 1) / SCAN_TILE + 1);
+		g.scan_status = carve<uint32_t>(chunk, scan_status_words(P));
 		g.sort_scratch_bytes = ::psb::sort_scratch_bytes(P, 4);
 		g.sort_scratch = carve<char>(chunk, g.sort_scratch_bytes);
 		return g;

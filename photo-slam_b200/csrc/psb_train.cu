@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(TB, PSB_A_MINBLOCKS) gaussian_backward_kernel(
 			mr = reinterpret_cast<const float4*>(t.m[5])[idx]; vr = reinterpret_cast<const float4*>(t.v[5])[idx];
 		}
 		if (st.enabled) { st_rad = st.max_radii2D[idx]; st_acc = st.xyz_gradient_accum[idx]; st_den = st.denom[idx]; }
-		const uint32_t tt = geom.tiles_touched[idx];
+		const uint32_t tt = geom.tile_info[idx].z;
 		const float4 s0 = sink[3 * idx], s1 = sink[3 * idx + 1], s2 = sink[3 * idx + 2];
 		const uint32_t meta = __float_as_uint(geom.rec[idx].q2.w);
 #pragma unroll

@@ -156,9 +156,9 @@ int forward_raw(psb_trainer* t, int P, int M, int D, const psb_model* model, con
 	t->mark(0, stream);
 	if ((rc = launch_preprocess(in, cam, radii, geom, /*raw=*/true, t->tight, stream))) return rc;
 	t->mark(1, stream);
-	if ((rc = launch_depth_sort_and_scan(P, geom, stream))) return rc;
+	if ((rc = launch_depth_sort_and_scan(P, geom, /*scan=*/false, stream))) return rc;
 	t->mark(2, stream);
-	if ((rc = launch_binning(P, cam, geom, bin, img, geom.counters, t->capacity, t->tight, stream))) return rc;
+	if ((rc = launch_scan_binning(P, cam, geom, bin, img, t->capacity, t->tight, stream))) return rc;
 	t->mark(3, stream);
 	// the instance count travels to pinned memory as soon as it exists: psb_trainer_result waits on `readback`, not on the stream
 	PSB_CUDA_OK(cudaMemcpyAsync(t->h_count, geom.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
