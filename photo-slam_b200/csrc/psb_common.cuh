@@ -195,11 +195,42 @@ struct TileCull {
 		}
 		return !(qmin > thr + pad);
 	}
-	// tile (tx, ty) of a W x H image
-	__device__ __forceinline__ bool hit(int tx, int ty, int W, int H) const
+	// Bit k (row-major) = tile k of the tile rectangle [x0,x1) x [y0,y1) (at most 32 tiles) of a W x H image can be reached.
+	// Same test as reaches() per tile, with the row-only terms hoisted and ONE rounding pad for the whole rectangle
+	// (evaluated at the largest |dx|, |dy| of the rectangle, hence >= every per-tile pad: keeps a superset).
+	__device__ __forceinline__ uint32_t rect_mask(int x0, int y0, int x1, int y1, int W, int H) const
 	{
-		const int x0 = tx * PSB_TILE_X, y0 = ty * PSB_TILE_Y;
-		return reaches((float)x0, (float)y0, (float)(min(x0 + PSB_TILE_X, W) - 1), (float)(min(y0 + PSB_TILE_Y, H) - 1));
+		const int area = (x1 - x0) * (y1 - y0);
+		const uint32_t full = area >= 32 ? 0xffffffffu : ((1u << area) - 1u);
+		if (none) return 0u;
+		if (all) return full;
+		const float DX = fmaxf(fabsf(mx - (float)(x0 * PSB_TILE_X)), fabsf(mx - (float)(min(x1 * PSB_TILE_X, W) - 1)));
+		const float DY = fmaxf(fabsf(my - (float)(y0 * PSB_TILE_Y)), fabsf(my - (float)(min(y1 * PSB_TILE_Y, H) - 1)));
+		const float thrp = thr + __fmaf_rn(1e-5f, splat_q(A, fabsf(B), C, DX, DY), 1e-4f);
+		uint32_t mask = 0u, bit = 1u;
+		for (int ty = y0; ty < y1; ty++) {
+			const int py0 = ty * PSB_TILE_Y;
+			const float dylo = my - (float)(min(py0 + PSB_TILE_Y, H) - 1), dyhi = my - (float)py0;
+			const bool yin = dylo <= 0.f && dyhi >= 0.f;
+			const float ey = dylo > 0.f ? dylo : dyhi;  // horizontal edge facing the centre (when !yin)
+			const float sxu = nba * ey, by = B * ey, cy = 0.5f * C * ey * ey;
+			for (int tx = x0; tx < x1; tx++, bit <<= 1) {
+				const int px0 = tx * PSB_TILE_X;
+				const float dxlo = mx - (float)(min(px0 + PSB_TILE_X, W) - 1), dxhi = mx - (float)px0;
+				const bool xin = dxlo <= 0.f && dxhi >= 0.f;
+				float qmin = (xin && yin) ? 0.f : 3.0e38f;
+				if (!xin) {
+					const float ex = dxlo > 0.f ? dxlo : dxhi;
+					qmin = splat_q(A, B, C, ex, fminf(fmaxf(nbc * ex, dylo), dyhi));
+				}
+				if (!yin) {
+					const float s2 = fminf(fmaxf(sxu, dxlo), dxhi);
+					qmin = fminf(qmin, __fmaf_rn(__fmaf_rn(0.5f * A, s2, by), s2, cy));
+				}
+				if (!(qmin > thrp)) mask |= bit;
+			}
+		}
+		return mask;
 	}
 };
 __device__ __forceinline__ bool splat_reaches_tile(const float4 q0, const float4 q1, float px0, float py0, float px1, float py1)

@@ -173,11 +173,7 @@ __global__ void __launch_bounds__(PRE_TB) preprocess_fwd_kernel(GaussIn in, Came
 		// get an instance. The blend skips such instances anyway (reference forward.cu:338-339 `alpha < 1/255 -> continue`),
 		// so the image and every gradient are unchanged; the lists the sort and the blend walk shrink by about a third.
 		if ((int)count <= TIGHT_MAX_AREA) {
-			const TileCull cull(r.q0, r.q1);
-			uint32_t bit = 1;
-			mask = 0;
-			for (int ty = y0; ty < y1; ty++)
-				for (int tx = x0; tx < x1; tx++, bit <<= 1) mask |= cull.hit(tx, ty, cam.W, cam.H) ? bit : 0u;
+			mask = TileCull(r.q0, r.q1).rect_mask(x0, y0, x1, y1, cam.W, cam.H);
 			count = (uint32_t)__popc(mask);
 		}
 		count |= TT_VISIBLE;
@@ -359,7 +355,10 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32
 // one contiguous, coalesced run. counters[0] <- total instance count; instances beyond `capacity` are not written (the
 // step then degrades to a no-op, see psb_trainer.cu).
 constexpr int EM_THREADS = 256, EM_ITEMS = 4, EM_TILE = EM_THREADS * EM_ITEMS;
-constexpr int EM_STAGE = 5120;  // instances staged per block (40 KB); a block with more writes to global memory directly
+#ifndef PSB_EM_STAGE
+#define PSB_EM_STAGE 5120
+#endif
+constexpr int EM_STAGE = PSB_EM_STAGE;  // instances staged per block (40 KB); a block with more writes to global memory directly
 template <bool TIGHT>
 __global__ void __launch_bounds__(EM_THREADS) emit_scan_kernel(int P, const uint32_t* __restrict__ order, const uint4* __restrict__ tile_info,
                                                                uint32_t* __restrict__ tile_key, uint32_t* __restrict__ inst, int grid_x,

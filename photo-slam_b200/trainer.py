@@ -136,6 +136,27 @@ class GaussianModel:
             dst.copy_(src)
         self.step_, self.lr_, self.active_sh_degree_ = snap["step"], list(snap["lr"]), snap["sh"]
 
+    # --- on-disk point cloud (reference GaussianModel::savePly / loadPly / saveSparsePointsPly, gaussian_model.cpp:838-1088)
+    def savePly(self, path):
+        from . import io
+        io.save_ply(path, *[t.detach().cpu().numpy() for t in self.tensors()])
+
+    def loadPly(self, path):
+        """Replaces the parameter tensors by the file's content and activates every SH degree (gaussian_model.cpp:951)."""
+        from . import io
+        a = io.load_ply(path, self.max_sh_degree_)
+        t = lambda x: torch.from_numpy(x).to(self.device).contiguous()
+        self._set([t(a[k]) for k in ("xyz", "features_dc", "features_rest", "opacity", "scaling", "rotation")])
+        self.active_sh_degree_ = self.max_sh_degree_
+
+    def setSparsePoints(self, xyz, color):
+        """sparse SLAM map points + colours in [0,1] kept for input.ply (reference gaussian_model.cpp: sparse_points_xyz_ / _color_)"""
+        self.sparse_points_xyz_, self.sparse_points_color_ = xyz, color
+
+    def saveSparsePointsPly(self, path):
+        from . import io
+        io.save_sparse_points_ply(path, self.sparse_points_xyz_.cpu().numpy(), self.sparse_points_color_.cpu().numpy())
+
     def exponLrFunc(self, step):
         if step < 0 or (self.lr_init_ == 0.0 and self.lr_final_ == 0.0):
             return 0.0
@@ -320,7 +341,9 @@ class GaussianTrainer:
         s.update_densify_stats = int(densify_stats)
         return s
 
-    def render(self, cam, out=None, radii=None):
+    def render(self, cam, out=None, radii=None, check=True):
+        """Forward only. check=True waits for the instance count and renders again if the binning arena had to grow (an
+        overflowing render leaves `out` blank); pass check=False to only enqueue (call result() yourself before using `out`)."""
         m = self.model
         out = out if out is not None else torch.empty((3, cam["H"], cam["W"]), device=m.device)
         cm, cc = m._cmodel(False), _ccamera(cam)
@@ -329,6 +352,8 @@ class GaussianTrainer:
                                              torch.cuda.current_stream().cuda_stream), "psb_trainer_render")
         self._last_render = (cam, out, radii)
         self._last = None
+        if check:
+            self.result()
         return out
 
     def trainForOneIteration(self, cam, gt_image, mask=None, out_color=None, radii=None, densify_stats=None):
@@ -352,7 +377,7 @@ class GaussianTrainer:
         rc = self.L.psb_trainer_result(self.h, out, C.byref(n), torch.cuda.current_stream().cuda_stream)
         if rc == -4 and getattr(self, "_last", None) is None:  # a render overflowed the arena: render again
             cam, o, rad = self._last_render
-            self.render(cam, o, rad)
+            self.render(cam, o, rad, check=False)
             return self.result()
         if rc == -4:  # PSB_ERR_RETRY: the step was a no-op
             self.model.step_ -= 1
