@@ -145,6 +145,15 @@ def cpu_baseline():
             "sample": f"config A (50k Gaussians, 640x480): {n} x (forward + backward) of oracle/gs_oracle.c, OpenMP on the per-Gaussian and forward-blend loops; no loss/Adam"}
 
 
+# ncu DRAM bytes per iteration of each stage at config D (profiles/r1_ncu_full_step_metrics.csv, round 1 final kernels)
+NCU_DRAM_BYTES_CONFIG_D = {"preprocess": 0.882e9, "depth_sort_scan": 0.099e9, "binning": None, "render_fwd": 0.081e9, "loss": 0.070e9,
+                           "render_bwd": 0.111e9, "backward_adam": 5.754e9}
+STAGE_KERNELS = {"preprocess": ["preprocess_fwd_kernel"], "depth_sort_scan": ["rs_histogram_kernel", "rs_scan_hist_kernel", "rs_onesweep_kernel x4"],
+                 "binning": ["emit_scan_kernel", "rs_histogram_kernel", "rs_scan_hist_kernel", "rs_onesweep_kernel x2", "tile_ranges_kernel"],
+                 "render_fwd": ["render_fwd_kernel"], "loss": ["loss_fwd_kernel", "loss_bwd_kernel"], "render_bwd": ["render_bwd_kernel"],
+                 "backward_adam": ["gaussian_backward_kernel", "frest_stream_kernel"]}
+
+
 def algorithmic_bytes(P, P_vis, N, W, H, T):
     """SURVEY.md §8(d) per-unit figures x units of this workload, per stage of psb_trainer_step (bytes)."""
     return {
@@ -271,10 +280,14 @@ def run_psb(args, world, rank, local, dev):
                        for k in stages}
         top = max(stages, key=stages.get)
         roof = {"kernel": top, "bound": "hbm", "achieved": stage_table[top]["GBps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": stage_table[top]["frac_of_hbm_peak"], "traffic": None,
+                "frac": stage_table[top]["frac_of_hbm_peak"],
+                # dram__bytes_read.sum + dram__bytes_write.sum of the stage's launches, one `ncu --set full` capture of this
+                # workload (profiles/r1_ncu_full_step_metrics.csv); null for any other workload
+                "traffic": NCU_DRAM_BYTES_CONFIG_D.get(top) if (P == 3_000_000 and args.camera == "replica") else None,
+                "launches": STAGE_KERNELS.get(top),
                 "note": "achieved = SURVEY §8(d) algorithmic bytes of the stage / its CUDA-event time inside psb_trainer_step; see stages for every stage"}
 
-    launches_per_step = 19 if world == 1 else 25  # kernels of this library per iteration (memsets not counted)
+    launches_per_step = 19 if world == 1 else 17 + 4 * (2 + 6)  # kernels of this library per iteration (memsets not counted); DP: 4 slabs x (2 backward + 6 Adam)
     out = {
         "metric": "train_iters_per_sec", "value": world * 1000.0 / ms_step, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
