@@ -35,3 +35,38 @@ def test_scene_statistics():
     assert 0.03 < np.mean(z <= 0.2) < 0.07                                  # ~5 % behind the near plane
     sig_px = np.exp(sc["scaling"]).mean(1) * fx / np.maximum(np.abs(z), 0.5)
     assert 2.0 < np.median(sig_px) < 3.5
+
+
+def test_model_snapshot_restore_and_ply_roundtrip_on_cpu(tmp_path):
+    """Host-side GaussianModel logic that needs no kernel: training-state snapshot / restore (used by bench.py to time every leg on
+    the same iterations), LR schedule, savePly / loadPly (reference gaussian_model.cpp:838-1056) on CPU tensors."""
+    import torch
+    from photo_slam_b200 import trainer
+    W, H, fx, fy = syn.CAMERAS["tum"]
+    cam = syn.make_camera(W, H, fx, fy)
+    sc = syn.make_scene(300, cam, seed=1)
+    m = trainer.GaussianModel.from_numpy(sc, "cpu")
+    opt = trainer.GaussianOptimizationParams()
+    m.trainingSetup(opt)
+    snap = m.snapshot()
+    ptrs = [t.data_ptr() for t in m.tensors()]
+    for t in m.tensors() + m.exp_avg_ + m.exp_avg_sq_:
+        t.add_(1.0)
+    m.step_, m.lr_[0] = 7, 123.0
+    m.restore(snap)
+    assert [t.data_ptr() for t in m.tensors()] == ptrs                      # restored in place: device pointers stay valid
+    assert m.step_ == 0 and m.lr_[0] == opt.position_lr_init * m.spatial_lr_scale_
+    for t, k in zip(m.tensors(), ("xyz", "features_dc", "features_rest", "opacity", "scaling", "rotation")):
+        assert np.array_equal(t.numpy(), sc[k]), k
+    assert not any(t.any() for t in m.exp_avg_ + m.exp_avg_sq_)
+    # log-linear position learning rate (gaussian_model.cpp:1118-1131)
+    assert math.isclose(m.exponLrFunc(0), m.lr_init_, rel_tol=1e-6) and math.isclose(m.exponLrFunc(m.max_steps_), m.lr_final_, rel_tol=1e-6)
+    mid = m.exponLrFunc(m.max_steps_ // 2)
+    assert math.isclose(mid, math.sqrt(m.lr_init_ * m.lr_final_), rel_tol=1e-3)
+    path = str(tmp_path / "pc.ply")
+    m.savePly(path)
+    m2 = trainer.GaussianModel(3, "cpu")
+    m2.loadPly(path)
+    assert m2.active_sh_degree_ == 3
+    for a, b in zip(m.tensors(), m2.tensors()):
+        assert a.shape == b.shape and torch.equal(a, b)
