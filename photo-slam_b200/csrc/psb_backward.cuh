@@ -1,5 +1,5 @@
 // Device functions of the per-Gaussian backward, shared by the stand-alone backward kernel (psb_backward.cu)
-// and the fused backward + Adam kernel of the trainer step (psb_train.cu).
+// and the per-Gaussian backward + Adam kernel of the trainer step (psb_train.cu).
 // Math follows reference cuda_rasterizer/backward.cu:20-139 (SH), :144-274 (cov2D), :278-341 (cov3D), :346-396.
 #pragma once
 #include "psb_geom.cuh"

@@ -3,7 +3,7 @@
 // Per digit pass every thread block
 //   1. takes a ticket (atomic) so tiles are processed in a globally monotonic order,
 //   2. loads 4096 keys (16 per thread, warp-striped, fully coalesced) into registers,
-//   3. ranks them per warp with __match_any_sync on the digit (stable inside the warp chunk),
+//   3. ranks them per warp with one ballot per digit bit + one shared-memory atomic per run (stable inside the warp chunk),
 //   4. turns per-warp digit counts into per-block counts, publishes them and resolves the cross-block
 //      prefix per digit by decoupled look-back (one 32-bit status word = 2 flag bits + 30-bit count),
 //   5. reorders keys/values through shared memory so each digit's run leaves as a contiguous,

@@ -295,8 +295,6 @@ __global__ void adam_tail_kernel(size_t start, size_t n, float* p, float* m, flo
 
 }  // namespace
 
-size_t fused_backward_smem_bytes(bool) { return 0; }  // static shared memory only
-
 int launch_fused_backward(bool adam, int first, int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, float* seeds,
                           const StepHyper& h, const GradSegments& grads, const DensifyStats& st, const uint32_t* counters, uint32_t capacity,
                           cudaStream_t stream)

@@ -29,7 +29,6 @@ struct DensifyStats {
 	float* denom;               // [P,1]
 };
 
-size_t fused_backward_smem_bytes(bool adam);
 // Gaussians [first, P) (first must be a multiple of 128 so f_rest chunks stay 16-byte aligned)
 // seeds: scratch [P][20] floats (per-Gaussian SH gradient seeds handed from the per-Gaussian kernel to the f_rest stream kernel)
 int launch_fused_backward(bool adam, int first, int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, float* seeds,
