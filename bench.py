@@ -41,7 +41,14 @@ def parse():
     ap.add_argument("--points", type=int, default=3_000_000)
     ap.add_argument("--camera", default="replica")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--config", default=None, choices=["B", "C", "D"],
+                    help="BASELINE.json config shorthand: B = 500k Gaussians / replica 1200x680, C = 1M / tum 640x480, D = 3M / replica (default)")
+    ap.add_argument("--dp-mode", default=None, choices=["p2p", "nccl"], help="N > 1: fused NVLink step (default) or the NCCL all-reduce path")
+    a = ap.parse_args()
+    if a.config:
+        a.points, a.camera = {"B": (500_000, "replica"), "C": (1_000_000, "tum"), "D": (3_000_000, "replica")}[a.config]
+    a.config = a.config or {(500_000, "replica"): "B", (1_000_000, "tum"): "C", (3_000_000, "replica"): "D"}.get((a.points, a.camera), "custom")
+    return a
 
 
 class ClockSampler:
@@ -201,7 +208,8 @@ def run_psb(args, world, rank, local, dev):
     scene, cam, host, devcam, gt_dev = make_inputs(args, rank, dev)
     model = T.GaussianModel.from_numpy(scene, dev)
     model.trainingSetup(T.GaussianOptimizationParams())
-    tr = T.DataParallelTrainer(model) if world > 1 else T.GaussianTrainer(model)
+    tr = T.DataParallelTrainer(model, mode=args.dp_mode) if world > 1 else T.GaussianTrainer(model)
+    dp_mode = tr.mode if world > 1 else None
     P, W, H = args.points, devcam["W"], devcam["H"]
     radii = torch.zeros(P, dtype=torch.int32, device=dev)
 
@@ -215,9 +223,17 @@ def run_psb(args, world, rank, local, dev):
     snap, it0 = model.snapshot(), tr.iteration
 
     def rewind():
+        if world > 1:
+            tr.sync()                # every peer's rows of the last step have landed here ...
+            barrier(world)           # ... and nobody is still pushing when the replicas are rewound
         model.restore(snap)
         tr.iteration = it0
-        torch.cuda.synchronize()
+        barrier(world)
+
+    if world > 1:
+        tr.sync()
+        barrier(world)
+        snap = model.snapshot()      # (moments: each rank snapshots and restores its own rows)
 
     # --- value: K iterations, inputs resident in HBM, no host sync inside (parameters + moments = 2.1 GB >> L2)
     barrier(world)
@@ -226,10 +242,14 @@ def run_psb(args, world, rank, local, dev):
         e0.record()
         for _ in range(args.steps):
             tr.trainForOneIteration(devcam, gt_dev)
+        if world > 1:
+            tr.sync()                # the step is complete when every rank's rows have landed (device-side wait, inside the timed region)
         e1.record()
         barrier(world)
         ms_total = max_over_ranks(e0.elapsed_time(e1), world, dev)
-    tr.result()
+    tr.result()                      # raises if any of the K queued steps overflowed the binning arena (sticky device-side record)
+    if world > 1:
+        assert tr.dropped_views == 0 and tr.status() == 0, "a timed step dropped its view or a cross-rank wait timed out"
     clocks = clk.summary()
     ms_step = ms_total / args.steps
 
@@ -267,6 +287,7 @@ def run_psb(args, world, rank, local, dev):
                 stage[k].copy_(host[k], non_blocking=True)
             tr.trainForOneIteration(cam2, stage["gt"])
             loss_host = tr.result()[0]          # device -> host read of the step's loss (blocks, like loss.item())
+        tr.sync()
         e1.record()
         barrier(world)
     ms_e2e = max_over_ranks(e0.elapsed_time(e1), world, dev) / args.steps
@@ -316,16 +337,21 @@ def run_psb(args, world, rank, local, dev):
                 "launches": STAGE_KERNELS.get(top),
                 "note": "achieved = SURVEY §8(d) algorithmic bytes of the stage / its CUDA-event time inside psb_trainer_step; see stages for every stage"}
 
-    launches_per_step = 19 if world == 1 else 17 + 4 * (2 + 6)  # kernels of this library per iteration (memsets not counted); DP: 4 slabs x (2 backward + 6 Adam)
+    # kernels of this library per iteration (memsets not counted). p2p: 17 up to the tile backward + param-flag wait + push backward
+    # + grad-flag wait + 2 owner-side Adam kernels; nccl: 4 slabs x (2 backward + 6 Adam)
+    launches_per_step = 19 if world == 1 else (17 + 5 if dp_mode == "p2p" else 17 + 4 * (2 + 6))
     out = {
         "metric": "train_iters_per_sec", "value": world * 1000.0 / ms_step, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "impl": "psb",
-        "config": {"workload": f"D: synthetic {P} Gaussians (SURVEY 8d, seed 0), {W}x{H} {args.camera} intrinsics, SH degree 3, 1 view/GPU/step, "
+        "config": {"workload": f"{args.config}: synthetic {P} Gaussians (SURVEY 8d, seed 0), {W}x{H} {args.camera} intrinsics, SH degree 3, 1 view/GPU/step, "
                                "render + L1+0.2DSSIM + backward + densify stats + Adam(59 floats/Gaussian)",
                    "gaussians": P, "visible": P_vis, "num_rendered": n_inst, "width": W, "height": H,
                    "l2_policy": "working set (2.1 GB of parameters + moments per step) is larger than L2; no explicit flush",
-                   "parallelism": "single GPU" if world == 1 else f"replicated scene, keyframe-sharded, NCCL all-reduce of [P,59] gradients x{world}"},
+                   "parallelism": "single GPU" if world == 1 else (
+                       f"replicated scene, keyframe-sharded x{world}; fused NVLink step: 80 B gradient records pushed to the owner rank, sharded Adam, updated rows "
+                       "stored to every replica (peer memory, no collective)" if dp_mode == "p2p" else
+                       f"replicated scene, keyframe-sharded, NCCL all-reduce of [P,59] gradients x{world}")},
         "e2e": {"value": world * 1000.0 / ms_e2e, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 20},
         "render_mpix_per_s": W * H / 1e6 / (render_ms / 1e3), "render_ms": render_ms,
         "gpu_launches": launches_per_step * args.steps, "loss": loss_host, "clocks": clocks,
@@ -410,7 +436,7 @@ def run_reference(args, dev):
         "metric": "train_iters_per_sec", "value": val, "unit": "iters/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "impl": "reference",
-        "config": {"workload": f"D: synthetic {P} Gaussians (SURVEY 8d, seed 0), {W}x{H} {args.camera} intrinsics, SH degree 3, 1 view/step, "
+        "config": {"workload": f"{args.config}: synthetic {P} Gaussians (SURVEY 8d, seed 0), {W}x{H} {args.camera} intrinsics, SH degree 3, 1 view/step, "
                                "render + L1+0.2DSSIM + backward + densify stats + Adam(59 floats/Gaussian)",
                    "gaussians": P, "visible": P_vis, "width": W, "height": H,
                    "reference_path": "reference cuda_rasterizer kernels (unmodified, sm_100a) + ATen ops of the reference's LibTorch host loop, on the GPU"},

@@ -183,14 +183,58 @@ int psb_trainer_backward_slab(psb_trainer* t, int P, int M, const psb_model* mod
 int psb_adam_flat(size_t n, float* param, float* exp_avg, float* exp_avg_sq, const float* grad, float lr,
                   const psb_step* step, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Keyframe-sharded data parallelism over NVLink peer memory: one process per GPU, replicated
+ * Gaussians, rank r trains on its own view, K views per optimizer step (mean gradient). Replaces the
+ * optimizer step of the reference iteration (src/gaussian_mapper.cpp:769-772) at world > 1 by a fused
+ *   reduce-scatter (80-byte gradient records pushed by the per-Gaussian backward straight into the owner
+ *   rank's inbox) -> Adam on the owned rows only (moments live on the owner) -> all-gather (the owner's Adam
+ *   kernels store the updated rows into every rank's parameter tensors)
+ * with no materialised reduced gradient and no collective call. Ownership: chunks of 128 Gaussians, chunk c
+ * belongs to rank c % world. The six parameter tensors must live in this context's arena (psb_dp_params), which
+ * is mapped into the peers with CUDA IPC: create on every rank -> exchange the psb_dp_ipc_handle blobs with any
+ * host-side transport (torch.distributed, MPI, a socket) -> psb_dp_connect. Moments (psb_model.exp_avg*) stay
+ * ordinary full-size tensors; only the rows this rank owns are read or written.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct psb_dp psb_dp;
+int psb_dp_create(psb_dp** out, int rank, int world, int P);   /* world <= 8; every rank must pass the same P */
+int psb_dp_handle_bytes(void);                                 /* size of one IPC handle blob (64) */
+int psb_dp_ipc_handle(psb_dp* dp, void* out_handle);           /* this rank's blob */
+int psb_dp_connect(psb_dp* dp, const void* handles);           /* world blobs, rank-major; no-op for world == 1 */
+int psb_dp_params(psb_dp* dp, float** out6);                   /* device addresses of the six parameter tensors in the arena (order of psb_model.param) */
+/* One data-parallel iteration: render -> loss -> tile backward -> per-Gaussian backward with records pushed to the
+ * owners -> (device-side wait for every rank's records) -> Adam of the owned rows, updated rows stored to every rank.
+ * Asynchronous: no host synchronisation, every cross-rank dependency is a device-side wait on an epoch flag. A view
+ * whose binning arena overflows contributes a zero gradient to the step (psb_trainer_result still reports
+ * PSB_ERR_RETRY and grows the arena): the replicas stay identical and no rank waits forever. */
+int psb_dp_step(psb_trainer* t, psb_dp* dp, int P, int M, const psb_model* model, const psb_camera* camera,
+                const float* background, const float* gt_image, const float* mask, const psb_step* step,
+                float* out_color, int* radii, void* stream);
+/* Enqueues a device-side wait until every rank's rows of the last psb_dp_step have landed in this rank's tensors. */
+int psb_dp_sync(psb_dp* dp, void* stream);
+/* 0 = healthy, 1 = a cross-rank wait timed out (PSB_DP_TIMEOUT_MS, default 20 s). Synchronises the stream. */
+int psb_dp_status(psb_dp* dp, void* stream);
+int psb_dp_destroy(psb_dp* dp);
+
 /* Returns the results of the last step / backward / render: out3 = {loss, l1, ssim} (host, may be NULL),
  * *num_rendered (may be NULL). Blocks only until those scalars have reached pinned host memory (an event recorded
  * right behind the loss kernel), NOT until the step has finished: the caller can read the loss of iteration i and
  * enqueue iteration i+1 while the backward half of i is still running. Use a stream/device synchronize to wait for
  * the step itself.
- * Returns PSB_ERR_RETRY when the binning arena was too small for that view: the step was a no-op on the
- * model, the arena has been grown, call the step again. */
+ * Returns PSB_ERR_RETRY when the binning arena was too small for a view SINCE THE LAST CALL of this function (the
+ * record is sticky on the device: a queued step that overflowed is reported even if later steps fitted): that step
+ * was a no-op on the model, the arena has been grown, call the step again. psb_trainer_overflow_info tells which
+ * call it was: sequence numbers count the forward passes (render / step / backward) of this context from 1;
+ * *first_seq = the first overflowing one, *count = how many overflowed, *current_seq = the latest pass enqueued. */
 int psb_trainer_result(psb_trainer* t, float* out3, int* num_rendered, void* stream);
+int psb_trainer_overflow_info(psb_trainer* t, unsigned* first_seq, unsigned* count, unsigned* current_seq);
+
+/* Parity/debug export (tests only) of the last step / render of this context: per pixel the final transmittance
+ * (final_T [H*W] f32, device, may be NULL) and the Gaussian index of the last blended splat (last_gauss [H*W] i32,
+ * device, -1 = none, may be NULL) — the trainer-path counterpart of psb_debug_export's n_contrib / final_T, comparable
+ * with the reference's point_list[ranges.x + n_contrib - 1] (cuda_rasterizer/forward.cu:352-365) even though the
+ * tight instance lists number their entries differently. *num_rendered (host, may be NULL) = instance count. */
+int psb_trainer_debug_state(psb_trainer* t, int width, int height, int* last_gauss, float* final_T, int* num_rendered, void* stream);
 
 /* Optional per-stage timing of psb_trainer_step with CUDA events recorded on the step's stream (bench.py uses
  * it for the roofline numbers; off by default). ms[0..6] = preprocess, depth sort + scan, binning (emit + tile

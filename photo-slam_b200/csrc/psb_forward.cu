@@ -433,10 +433,17 @@ __global__ void __launch_bounds__(EM_THREADS) emit_scan_kernel(int P, const uint
 
 // Start/end of every tile in the tile-sorted instance list (semantics of reference
 // rasterizer_impl.cu:116-138; ranges must be zeroed beforehand so untouched tiles read {0,0}).
+// ovf (trainer path, may be null): sticky record of overflowing views {count, first sequence number, largest instance count}
+// kept across steps until the host collects it (psb_trainer_result) — a queued step that degraded to a no-op stays detectable.
 __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ n_dev, uint32_t n_host, const uint32_t* __restrict__ tile_key_sorted,
-                                                          uint2* __restrict__ ranges)
+                                                          uint2* __restrict__ ranges, uint32_t* __restrict__ ovf, uint32_t seq)
 {
 	const uint32_t n = n_dev ? (*n_dev > n_host ? 0u : *n_dev) : n_host;
+	if (ovf && n_dev && blockIdx.x == 0 && threadIdx.x == 0 && *n_dev > n_host) {
+		atomicAdd(&ovf[0], 1u);
+		atomicMin(&ovf[1], seq);
+		atomicMax(&ovf[2], *n_dev);
+	}
 	for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
 		const uint32_t cur = tile_key_sorted[idx];
 		if (idx == 0) ranges[cur].x = 0;
@@ -509,7 +516,7 @@ int launch_binning(int P, const Camera& cam, const GeomState& geom, BinState& bi
 	int rc = radix_sort_pairs(bin.tile_key, bin.inst, false, nullptr, n_host, plan, bin.sort_scratch, bin.sort_scratch_bytes, stream);
 	if (rc) return rc;
 	const int res = plan.npass & 1;
-	tile_ranges_kernel<<<ranges_grid(n_host), 256, 0, stream>>>(nullptr, (uint32_t)n_host, bin.tile_key[res], img.ranges);
+	tile_ranges_kernel<<<ranges_grid(n_host), 256, 0, stream>>>(nullptr, (uint32_t)n_host, bin.tile_key[res], img.ranges, nullptr, 0u);
 	PSB_LAUNCH_OK();
 	return 0;
 }
@@ -517,7 +524,7 @@ int launch_binning(int P, const Camera& cam, const GeomState& geom, BinState& bi
 // Trainer path: scan + emit in one kernel, tile sort, ranges. The instance count stays on the device
 // (geom.counters[0]); `capacity` = size the binning chunk was carved for.
 int launch_scan_binning(int P, const Camera& cam, const GeomState& geom, BinState& bin, const ImgState& img, size_t capacity, bool tight,
-                        cudaStream_t stream)
+                        uint32_t* ovf, uint32_t seq, cudaStream_t stream)
 {
 	const int num_tiles = cam.grid_x * cam.grid_y;
 	PSB_CUDA_OK(cudaMemsetAsync(img.ranges, 0, (size_t)num_tiles * sizeof(uint2), stream));
@@ -533,7 +540,7 @@ int launch_scan_binning(int P, const Camera& cam, const GeomState& geom, BinStat
 	int rc = radix_sort_pairs(bin.tile_key, bin.inst, false, geom.counters, capacity, plan, bin.sort_scratch, bin.sort_scratch_bytes, stream);
 	if (rc) return rc;
 	const int res = plan.npass & 1;
-	tile_ranges_kernel<<<ranges_grid(capacity), 256, 0, stream>>>(geom.counters, (uint32_t)capacity, bin.tile_key[res], img.ranges);
+	tile_ranges_kernel<<<ranges_grid(capacity), 256, 0, stream>>>(geom.counters, (uint32_t)capacity, bin.tile_key[res], img.ranges, ovf, seq);
 	PSB_LAUNCH_OK();
 	return 0;
 }

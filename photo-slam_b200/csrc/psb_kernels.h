@@ -47,7 +47,7 @@ int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t*
 int launch_depth_sort_and_scan(int P, GeomState& geom, bool scan, cudaStream_t stream);
 int launch_binning(int P, const Camera& cam, const GeomState& geom, BinState& bin, const ImgState& img, size_t n_host, cudaStream_t stream);
 int launch_scan_binning(int P, const Camera& cam, const GeomState& geom, BinState& bin, const ImgState& img, size_t capacity, bool tight,
-                        cudaStream_t stream);
+                        uint32_t* ovf, uint32_t seq, cudaStream_t stream);
 int launch_render_forward(const Camera& cam, const uint2* ranges, const uint32_t* point_list, const GaussRec* rec, const float* bg,
                           float* out_color, float* final_T, uint32_t* n_contrib, cudaStream_t stream);
 int launch_render_backward(const Camera& cam, const uint2* ranges, const uint32_t* point_list, const GaussRec* rec, const float* bg,

@@ -494,11 +494,8 @@ template <int PPT>
 static int launch_bwd_t(const Camera& cam, const uint2* ranges, const uint32_t* point_list, const GaussRec* rec, const float* bg,
                         const float* final_T, const uint32_t* n_contrib, const float* dL_dpix, const GradSink& sink, cudaStream_t stream)
 {
-	static bool attr_set = false;
-	if (!attr_set) {
-		PSB_CUDA_OK(cudaFuncSetAttribute(render_bwd_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem<PPT>)));
-		attr_set = true;
-	}
+	// the attribute is per device (and cheap): set it on every launch rather than cache it in a process-wide flag
+	PSB_CUDA_OK(cudaFuncSetAttribute(render_bwd_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem<PPT>)));
 	dim3 grid(cam.grid_x, cam.grid_y, 1);
 	render_bwd_kernel<PPT><<<grid, TileGeom<PPT>::THREADS, sizeof(BwdSmem<PPT>), stream>>>(ranges, point_list, rec, cam.W, cam.H, bg, final_T, n_contrib,
 	                                                                                      dL_dpix, sink);

@@ -19,6 +19,7 @@
 #include "psb_train.h"
 #include <cstdlib>
 #include <cstdint>
+#include <cstring>
 
 namespace psb {
 
@@ -32,6 +33,11 @@ constexpr int REST = 45;       // floats per f_rest row (15 coefficients x 3 cha
 constexpr int SEED = 20;       // floats per seed row: w_1..w_15 at [0..14], masked dL/dRGB at [16..18]
 
 struct AdamCoef { float beta1, beta2, eps, inv_bc1, inv_bc2_sqrt; };
+
+// gaussian_backward_kernel modes
+constexpr int MODE_GRADS = 0;  // dense gradients of the raw parameters -> `grads` (NCCL data-parallel path / tests)
+constexpr int MODE_ADAM = 1;   // fused single-GPU step: parameters and moments updated in place
+constexpr int MODE_PUSH = 2;   // NVLink data-parallel step: 80-byte gradient records pushed into the owner rank's inbox
 
 // torch::optim::Adam single-tensor update (LibTorch adam.cpp): exp_avg.mul_(b1).add_(g, 1-b1);
 // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2); denom = exp_avg_sq.sqrt()/sqrt(bc2) + eps; p.addcdiv_(exp_avg, denom, -lr/bc1).
@@ -55,18 +61,22 @@ __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, flo
 // frest_stream_kernel expands them. The f_rest parameter rows the SH backward has to READ (view-direction term of
 // dL/dxyz) arrive by one TMA bulk copy per block; each thread walks its own row in shared memory (row stride 45 words:
 // bank-conflict free).
-template <bool ADAM>
+template <int MODE>
 __global__ void __launch_bounds__(TB, PSB_A_MINBLOCKS) gaussian_backward_kernel(int first, int P, TrainTensors t, Camera cam, GeomState geom, float4* __restrict__ sink,
                                                             StepHyper h, GradSegments grads, DensifyStats st,
-                                                            const uint32_t* __restrict__ counters, uint32_t capacity, float4* __restrict__ seeds)
+                                                            const uint32_t* __restrict__ counters, uint32_t capacity, float4* __restrict__ seeds,
+                                                            DpPush dp)
 {
+	constexpr bool ADAM = MODE == MODE_ADAM;
 	__shared__ __align__(128) float s_p[TB * REST];  // f_rest parameter rows of this block (TMA destination)
 	__shared__ __align__(16) float s_w[TB][SEED];    // seed rows of this block (copied out 128-bit coalesced at the end)
 	__shared__ __align__(8) uint64_t s_bar;
 
-	// A binning arena that turned out too small leaves the tile lists incomplete: make the step a no-op
-	// (the host sees the same counter, grows the arena and repeats the step).
-	if (counters[0] > capacity) return;
+	// A binning arena that turned out too small leaves the tile lists incomplete. Fused step: no-op (the host sees the
+	// same counter, grows the arena and repeats the step). Data-parallel modes: this view contributes a ZERO gradient to
+	// the step (every rank still takes part in the exchange, so the replicas stay identical and nobody waits forever).
+	const bool overflow = counters[0] > capacity;
+	if (ADAM && overflow) return;
 
 	const int tid = threadIdx.x;
 	const int base = first + blockIdx.x * TB;  // this launch covers Gaussians [first, P)
@@ -124,7 +134,7 @@ __global__ void __launch_bounds__(TB, PSB_A_MINBLOCKS) gaussian_backward_kernel(
 		for (int c = 0; c < 3; c++) { sp_xyz[c] = t.p[0][3 * idx + c]; sp_dc[c] = t.p[1][3 * idx + c]; sp_sc[c] = t.p[4][3 * idx + c]; }
 		sp_op = t.p[3][idx];
 		sp_rot = reinterpret_cast<const float4*>(t.p[5])[idx];
-		visible = tt != 0;
+		visible = tt != 0 && !overflow;
 		const float4 z = make_float4(0, 0, 0, 0);
 		sink[3 * idx] = z; sink[3 * idx + 1] = z; sink[3 * idx + 2] = z;  // ready for the next iteration
 		if (visible) {
@@ -186,10 +196,23 @@ __global__ void __launch_bounds__(TB, PSB_A_MINBLOCKS) gaussian_backward_kernel(
 			gm[1] = ((clamp_bits >> 1) & 1u) ? 0.f : dL_dcolor.y;
 			gm[2] = ((clamp_bits >> 2) & 1u) ? 0.f : dL_dcolor.z;
 		}
-		const int ncoef = (h.D + 1) * (h.D + 1);
+		if (MODE != MODE_PUSH) {
+			const int ncoef = (h.D + 1) * (h.D + 1);
 #pragma unroll
-		for (int k = 1; k < 16; k++) s_w[tid][k - 1] = (k < ncoef) ? w[k] : 0.f;
-		s_w[tid][15] = 0.f; s_w[tid][16] = gm[0]; s_w[tid][17] = gm[1]; s_w[tid][18] = gm[2]; s_w[tid][19] = 0.f;
+			for (int k = 1; k < 16; k++) s_w[tid][k - 1] = (k < ncoef) ? w[k] : 0.f;
+			s_w[tid][15] = 0.f; s_w[tid][16] = gm[0]; s_w[tid][17] = gm[1]; s_w[tid][18] = gm[2]; s_w[tid][19] = 0.f;
+		} else {
+			// gradient record of this Gaussian for its owner rank (see DpPush): the SH weights are NOT sent, the owner
+			// re-evaluates w_k(dir) from its bit-identical copy of xyz and this rank's camera centre
+			s_w[tid][0] = g_xyz.x; s_w[tid][1] = g_xyz.y; s_w[tid][2] = g_xyz.z;
+			s_w[tid][3] = g_dc.x; s_w[tid][4] = g_dc.y; s_w[tid][5] = g_dc.z;
+			s_w[tid][6] = g_opac;
+			s_w[tid][7] = g_scale.x; s_w[tid][8] = g_scale.y; s_w[tid][9] = g_scale.z;
+			s_w[tid][10] = g_rot.x; s_w[tid][11] = g_rot.y; s_w[tid][12] = g_rot.z; s_w[tid][13] = g_rot.w;
+			s_w[tid][14] = gm[0]; s_w[tid][15] = gm[1]; s_w[tid][16] = gm[2];
+			s_w[tid][17] = 0.f; s_w[tid][18] = 0.f;
+			s_w[tid][19] = __uint_as_float(visible ? dp.epoch : 0u);
+		}
 	}
 
 	// ---- the 14 small parameters of this Gaussian
@@ -216,7 +239,7 @@ __global__ void __launch_bounds__(TB, PSB_A_MINBLOCKS) gaussian_backward_kernel(
 			}
 			t.p[3][idx] = sp_op; t.m[3][idx] = mo; t.v[3][idx] = vo;
 			reinterpret_cast<float4*>(t.p[5])[idx] = sp_rot; reinterpret_cast<float4*>(t.m[5])[idx] = mr; reinterpret_cast<float4*>(t.v[5])[idx] = vr;
-		} else {
+		} else if (MODE == MODE_GRADS) {
 			grads.g[0][3 * idx] = g_xyz.x; grads.g[0][3 * idx + 1] = g_xyz.y; grads.g[0][3 * idx + 2] = g_xyz.z;
 			grads.g[1][3 * idx] = g_dc.x; grads.g[1][3 * idx + 1] = g_dc.y; grads.g[1][3 * idx + 2] = g_dc.z;
 			grads.g[3][idx] = g_opac;
@@ -226,10 +249,42 @@ __global__ void __launch_bounds__(TB, PSB_A_MINBLOCKS) gaussian_backward_kernel(
 	}
 	__syncthreads();
 
-	// seed rows of this block -> global, 128-bit coalesced
-	const float4* src = reinterpret_cast<const float4*>(&s_w[0][0]);
-	float4* dst = seeds + (size_t)base * (SEED / 4);
-	for (int i = tid; i < rows * (SEED / 4); i += TB) dst[i] = src[i];
+	if (MODE != MODE_PUSH) {
+		// seed rows of this block -> global, 128-bit coalesced
+		const float4* src = reinterpret_cast<const float4*>(&s_w[0][0]);
+		float4* dst = seeds + (size_t)base * (SEED / 4);
+		for (int i = tid; i < rows * (SEED / 4); i += TB) dst[i] = src[i];
+		return;
+	}
+	// MODE_PUSH: the block's records go straight into the inbox of the rank that owns this 128-Gaussian chunk (remote
+	// stores over NVLink: fire and forget, they overlap the arithmetic of the blocks still running). Rows this view does
+	// not see are not sent: their stale epoch word tells the owner to count them as zero.
+	{
+		const int chunk = base / TB;
+		const int owner = chunk % dp.world, lc = chunk / dp.world;
+		float4* dst = reinterpret_cast<float4*>(dp.inbox[owner]) + ((size_t)dp.rank * dp.nlocal_max + lc) * (TB * (SEED / 4));
+		const float4* src = reinterpret_cast<const float4*>(&s_w[0][0]);
+		for (int i = tid; i < rows * (SEED / 4); i += TB) {
+			if (__float_as_uint(s_w[i / (SEED / 4)][19]) == dp.epoch) dst[i] = src[i];
+		}
+		// "all my records of this step have landed": every thread fences its own remote stores, the last block of the grid
+		// publishes this rank's camera centre and then the epoch flag on every rank (threadFenceReduction pattern)
+		__threadfence_system();
+		__syncthreads();
+		if (tid == 0) {
+			const uint32_t prev = atomicAdd(dp.done_counter, 1u);
+			if (prev == gridDim.x - 1) {
+				*dp.done_counter = 0u;
+				__threadfence_system();
+				for (int j = 0; j < dp.world; j++) {
+					float* mt = dp.meta[j] + 8 * dp.rank;
+					mt[0] = cam.campos[0]; mt[1] = cam.campos[1]; mt[2] = cam.campos[2]; mt[3] = (float)h.D;
+				}
+				__threadfence_system();
+				for (int j = 0; j < dp.world; j++) *reinterpret_cast<volatile uint32_t*>(dp.grad_flag[j] + dp.rank) = dp.epoch;
+			}
+		}
+	}
 }
 
 // Adam over the f_rest rows of Gaussians [first, P) (ADAM) or their gradient written out
@@ -239,7 +294,7 @@ __global__ void __launch_bounds__(256) frest_stream_kernel(uint32_t e_first, uin
                                                            float* __restrict__ gout, const float* __restrict__ seeds, float lr_eff, AdamCoef ac,
                                                            const uint32_t* __restrict__ counters, uint32_t capacity)
 {
-	if (counters[0] > capacity) return;  // overflowing step: no-op (see gaussian_backward_kernel)
+	if (ADAM && counters[0] > capacity) return;  // overflowing fused step: no-op (see gaussian_backward_kernel; !ADAM: the seeds are zero)
 	const uint32_t e = e_first + 4u * (blockIdx.x * 256u + threadIdx.x);
 	if (e >= e_end) return;
 	uint32_t row = e / REST;
@@ -289,8 +344,196 @@ __global__ void __launch_bounds__(256) adam_kernel(size_t n4, float4* __restrict
 }
 __global__ void adam_tail_kernel(size_t start, size_t n, float* p, float* m, float* v, const float* g, float lr, AdamCoef c, float grad_scale)
 {
-	const size_t i = start + threadIdx.x;
+	const size_t i = start + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) adam1(p[i], m[i], v[i], g[i] * grad_scale, lr * c.inv_bc1, c);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------------
+// NVLink data-parallel step, owner side. After every rank's records of this epoch have landed (launch_wait_flags), the
+// owner of a chunk sums the <= world records of each of its rows, applies Adam to its rows only (moments exist only on the
+// owner) and writes the updated parameters into EVERY rank's parameter tensors (remote stores over NVLink): reduce-scatter,
+// sharded optimizer and all-gather without a materialised reduced gradient and without a collective call.
+// ------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sh_weights(int deg, const float3 pos, const float3 campos, float* w /*[16]*/)
+{
+	// same expressions as sh_backward_t (psb_backward.cuh): the owner reproduces the source rank's weights bit for bit
+	const float3 d = make_float3(pos.x - campos.x, pos.y - campos.y, pos.z - campos.z);
+	const float len = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+	const float x = d.x / len, y = d.y / len, z = d.z / len;
+	const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+	w[0] = kSH_C0;
+	w[1] = -kSH_C1 * y; w[2] = kSH_C1 * z; w[3] = -kSH_C1 * x;
+	w[4] = kSH_C2_0 * xy; w[5] = kSH_C2_1 * yz; w[6] = kSH_C2_2 * (2.f * zz - xx - yy); w[7] = kSH_C2_3 * xz; w[8] = kSH_C2_4 * (xx - yy);
+	w[9] = kSH_C3_0 * y * (3.f * xx - yy); w[10] = kSH_C3_1 * xy * z; w[11] = kSH_C3_2 * y * (4.f * zz - xx - yy);
+	w[12] = kSH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy); w[13] = kSH_C3_4 * x * (4.f * zz - xx - yy); w[14] = kSH_C3_5 * z * (xx - yy);
+	w[15] = kSH_C3_6 * x * (xx - 3.f * yy);
+	const int ncoef = (deg + 1) * (deg + 1);
+#pragma unroll
+	for (int k = 0; k < 16; k++) if (k >= ncoef) w[k] = 0.f;
+}
+
+// One block per owned chunk, one thread per Gaussian: the 14 small parameters (Adam + push) and the summed f_rest gradient row.
+__global__ void __launch_bounds__(TB) shard_adam_small_kernel(DpShard d, TrainTensors t, StepHyper h, float grad_scale)
+{
+	__shared__ __align__(16) float s_g[TB * REST];
+	const int tid = threadIdx.x, lc = blockIdx.x;
+	const int chunk = lc * d.world + d.rank;
+	const int idx = chunk * TB + tid;
+	const bool valid = idx < d.P;
+	AdamCoef ac;
+	ac.beta1 = h.beta1; ac.beta2 = h.beta2; ac.eps = h.eps; ac.inv_bc1 = h.inv_bc1; ac.inv_bc2_sqrt = 1.0f / h.bc2_sqrt;
+
+	float acc[14];
+	float G[REST];
+#pragma unroll
+	for (int i = 0; i < 14; i++) acc[i] = 0.f;
+#pragma unroll
+	for (int i = 0; i < REST; i++) G[i] = 0.f;
+	float sp_xyz[3] = {0, 0, 1}, sp_dc[3] = {0, 0, 0}, sp_sc[3] = {0, 0, 0}, sp_op = 0.f;
+	float4 sp_rot = make_float4(1, 0, 0, 0);
+	float m3[3][3], v3[3][3], mo = 0.f, vo = 0.f;
+	float4 mr = make_float4(0, 0, 0, 0), vr = mr;
+	if (valid) {
+		const int tsel[3] = {0, 1, 4};
+#pragma unroll
+		for (int a = 0; a < 3; a++)
+#pragma unroll
+			for (int c = 0; c < 3; c++) { m3[a][c] = t.m[tsel[a]][3 * idx + c]; v3[a][c] = t.v[tsel[a]][3 * idx + c]; }
+		mo = t.m[3][idx]; vo = t.v[3][idx];
+		mr = reinterpret_cast<const float4*>(t.m[5])[idx]; vr = reinterpret_cast<const float4*>(t.v[5])[idx];
+#pragma unroll
+		for (int c = 0; c < 3; c++) { sp_xyz[c] = t.p[0][3 * idx + c]; sp_dc[c] = t.p[1][3 * idx + c]; sp_sc[c] = t.p[4][3 * idx + c]; }
+		sp_op = t.p[3][idx];
+		sp_rot = reinterpret_cast<const float4*>(t.p[5])[idx];
+		const float3 pos = make_float3(sp_xyz[0], sp_xyz[1], sp_xyz[2]);
+		for (int s = 0; s < d.world; s++) {
+			const float4* r = reinterpret_cast<const float4*>(d.inbox) + (((size_t)s * d.nlocal_max + lc) * TB + tid) * (DP_REC / 4);
+			const float4 r4 = r[4];
+			if (__float_as_uint(r4.w) != d.epoch) continue;  // rank s did not see this Gaussian in this step
+			const float4 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3];
+			acc[0] += r0.x; acc[1] += r0.y; acc[2] += r0.z; acc[3] += r0.w;
+			acc[4] += r1.x; acc[5] += r1.y; acc[6] += r1.z; acc[7] += r1.w;
+			acc[8] += r2.x; acc[9] += r2.y; acc[10] += r2.z; acc[11] += r2.w;
+			acc[12] += r3.x; acc[13] += r3.y;
+			const float gm[3] = {r3.z, r3.w, r4.x};
+			const float* mt = d.meta + 8 * s;
+			float w[16];
+			sh_weights((int)mt[3], pos, make_float3(mt[0], mt[1], mt[2]), w);
+#pragma unroll
+			for (int k = 1; k < 16; k++)
+#pragma unroll
+				for (int ch = 0; ch < 3; ch++) G[3 * (k - 1) + ch] += w[k] * gm[ch];
+		}
+		const float gs = grad_scale;
+		const float lx = h.lr[0] * ac.inv_bc1, ld = h.lr[1] * ac.inv_bc1, lo = h.lr[3] * ac.inv_bc1, ls = h.lr[4] * ac.inv_bc1, lrr = h.lr[5] * ac.inv_bc1;
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			adam1(sp_xyz[c], m3[0][c], v3[0][c], acc[c] * gs, lx, ac);
+			adam1(sp_dc[c], m3[1][c], v3[1][c], acc[3 + c] * gs, ld, ac);
+			adam1(sp_sc[c], m3[2][c], v3[2][c], acc[7 + c] * gs, ls, ac);
+		}
+		adam1(sp_op, mo, vo, acc[6] * gs, lo, ac);
+		adam1(sp_rot.x, mr.x, vr.x, acc[10] * gs, lrr, ac);
+		adam1(sp_rot.y, mr.y, vr.y, acc[11] * gs, lrr, ac);
+		adam1(sp_rot.z, mr.z, vr.z, acc[12] * gs, lrr, ac);
+		adam1(sp_rot.w, mr.w, vr.w, acc[13] * gs, lrr, ac);
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			t.m[0][3 * idx + c] = m3[0][c]; t.v[0][3 * idx + c] = v3[0][c];
+			t.m[1][3 * idx + c] = m3[1][c]; t.v[1][3 * idx + c] = v3[1][c];
+			t.m[4][3 * idx + c] = m3[2][c]; t.v[4][3 * idx + c] = v3[2][c];
+		}
+		t.m[3][idx] = mo; t.v[3][idx] = vo;
+		reinterpret_cast<float4*>(t.m[5])[idx] = mr; reinterpret_cast<float4*>(t.v[5])[idx] = vr;
+		for (int j = 0; j < d.world; j++) {  // all-gather by remote stores: every replica receives the updated rows
+			float* const* pp = d.param[j];
+#pragma unroll
+			for (int c = 0; c < 3; c++) { pp[0][3 * idx + c] = sp_xyz[c]; pp[1][3 * idx + c] = sp_dc[c]; pp[4][3 * idx + c] = sp_sc[c]; }
+			pp[3][idx] = sp_op;
+			reinterpret_cast<float4*>(pp[5])[idx] = sp_rot;
+		}
+	}
+	// summed f_rest gradient row -> local scratch (coalesced through shared memory; row stride 45 words is conflict-free)
+#pragma unroll
+	for (int i = 0; i < REST; i++) s_g[tid * REST + i] = G[i] * grad_scale;
+	__syncthreads();
+	float4* dst = reinterpret_cast<float4*>(d.g_rest + (size_t)lc * (TB * REST));
+	const float4* src = reinterpret_cast<const float4*>(s_g);
+	for (int i = tid; i < TB * REST / 4; i += TB) dst[i] = src[i];
+	__threadfence_system();  // this block's remote stores are performed before the kernel can complete
+}
+
+// Adam over the f_rest rows of the owned chunks, one block per chunk (5760 floats), 128-bit accesses; the updated values go
+// to every rank. Rows nobody has ever seen (g = m = v = 0) are left alone: their Adam update is exactly zero.
+__global__ void __launch_bounds__(256) shard_adam_frest_kernel(DpShard d, TrainTensors t, float lr_eff, AdamCoef ac)
+{
+	const int lc = blockIdx.x;
+	const int chunk = lc * d.world + d.rank;
+	const size_t e0 = (size_t)chunk * (TB * REST);
+	const size_t e_end = (size_t)d.P * REST;
+	float* p = t.p[2];
+	float* m = t.m[2];
+	float* v = t.v[2];
+	const float* g = d.g_rest + (size_t)lc * (TB * REST);
+	for (int i = threadIdx.x; i < TB * REST / 4; i += 256) {
+		const size_t e = e0 + 4 * (size_t)i;
+		if (e >= e_end) break;
+		if (e + 4 <= e_end) {
+			const float4 gg = __ldcs(reinterpret_cast<const float4*>(g + 4 * i));
+			float4 mm = __ldcs(reinterpret_cast<const float4*>(m + e)), vv = __ldcs(reinterpret_cast<const float4*>(v + e));
+			const bool idle = gg.x == 0.f && gg.y == 0.f && gg.z == 0.f && gg.w == 0.f && mm.x == 0.f && mm.y == 0.f && mm.z == 0.f && mm.w == 0.f &&
+			                  vv.x == 0.f && vv.y == 0.f && vv.z == 0.f && vv.w == 0.f;
+			if (idle) continue;
+			float4 pp = __ldcs(reinterpret_cast<const float4*>(p + e));
+			adam1(pp.x, mm.x, vv.x, gg.x, lr_eff, ac);
+			adam1(pp.y, mm.y, vv.y, gg.y, lr_eff, ac);
+			adam1(pp.z, mm.z, vv.z, gg.z, lr_eff, ac);
+			adam1(pp.w, mm.w, vv.w, gg.w, lr_eff, ac);
+			__stcs(reinterpret_cast<float4*>(m + e), mm); __stcs(reinterpret_cast<float4*>(v + e), vv);
+			for (int j = 0; j < d.world; j++) *reinterpret_cast<float4*>(d.param[j][2] + e) = pp;
+		} else {  // < 4 trailing elements (P * 45 not a multiple of 4)
+			for (size_t k = e; k < e_end; k++) {
+				float pp = p[k], mm = m[k], vv = v[k];
+				adam1(pp, mm, vv, g[k - e0], lr_eff, ac);
+				m[k] = mm; v[k] = vv;
+				for (int j = 0; j < d.world; j++) d.param[j][2][k] = pp;
+			}
+		}
+	}
+	// "my updated rows have landed everywhere": last block of the grid raises this rank's flag on every rank
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const uint32_t prev = atomicAdd(d.done_counter, 1u);
+		if (prev == gridDim.x - 1) {
+			*d.done_counter = 0u;
+			__threadfence_system();
+			for (int j = 0; j < d.world; j++) *reinterpret_cast<volatile uint32_t*>(d.param_flag[j] + d.rank) = d.epoch;
+		}
+	}
+}
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	return t;
+}
+
+// One warp: lane r waits for flags[r] >= epoch (written by rank r over NVLink). Bounded: a peer that never arrives (crashed
+// process) must not hang this GPU — after timeout_ns the kernel records the failure and returns.
+__global__ void wait_flags_kernel(const uint32_t* flags, int world, uint32_t epoch, uint32_t* status, unsigned long long timeout_ns)
+{
+	const int lane = threadIdx.x;
+	if (lane >= world) return;
+	const volatile uint32_t* f = flags + lane;
+	const unsigned long long t0 = global_timer_ns();
+	while ((int32_t)(*f - epoch) < 0) {
+		__nanosleep(200);
+		if (global_timer_ns() - t0 > timeout_ns) { atomicExch(status, 1u); break; }
+	}
+	__threadfence_system();
 }
 
 }  // namespace
@@ -305,8 +548,10 @@ int launch_fused_backward(bool adam, int first, int P, const TrainTensors& t, co
 	float4* sink4 = reinterpret_cast<float4*>(sink);
 	if (!seeds) { set_error_msg("launch_fused_backward: seed scratch missing"); return -1; }
 	if ((size_t)P * REST >= (size_t)UINT32_MAX - 8) { set_error_msg("psb_trainer: too many Gaussians for 32-bit element indices"); return -1; }
-	if (adam) gaussian_backward_kernel<true><<<grid, TB, 0, stream>>>(first, P, t, cam, geom, sink4, h, grads, st, counters, capacity, sd4);
-	else gaussian_backward_kernel<false><<<grid, TB, 0, stream>>>(first, P, t, cam, geom, sink4, h, grads, st, counters, capacity, sd4);
+	DpPush nodp;
+	memset(&nodp, 0, sizeof(nodp));
+	if (adam) gaussian_backward_kernel<MODE_ADAM><<<grid, TB, 0, stream>>>(first, P, t, cam, geom, sink4, h, grads, st, counters, capacity, sd4, nodp);
+	else gaussian_backward_kernel<MODE_GRADS><<<grid, TB, 0, stream>>>(first, P, t, cam, geom, sink4, h, grads, st, counters, capacity, sd4, nodp);
 	PSB_LAUNCH_OK();
 	AdamCoef ac;
 	ac.beta1 = h.beta1; ac.beta2 = h.beta2; ac.eps = h.eps; ac.inv_bc1 = h.inv_bc1; ac.inv_bc2_sqrt = 1.0f / h.bc2_sqrt;
@@ -314,6 +559,38 @@ int launch_fused_backward(bool adam, int first, int P, const TrainTensors& t, co
 	const unsigned gridB = (unsigned)(((size_t)(e1 - e0) + 1023) / 1024);
 	if (adam) frest_stream_kernel<true><<<gridB, 256, 0, stream>>>(e0, e1, t.p[2], t.m[2], t.v[2], nullptr, seeds, h.lr[2] * ac.inv_bc1, ac, counters, capacity);
 	else frest_stream_kernel<false><<<gridB, 256, 0, stream>>>(e0, e1, nullptr, nullptr, nullptr, grads.g[2], seeds, 0.f, ac, counters, capacity);
+	PSB_LAUNCH_OK();
+	return 0;
+}
+
+int launch_push_backward(int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, const StepHyper& h,
+                         const DensifyStats& st, const uint32_t* counters, uint32_t capacity, const DpPush& dp, cudaStream_t stream)
+{
+	if (P <= 0) return 0;
+	GradSegments nog;
+	memset(&nog, 0, sizeof(nog));
+	gaussian_backward_kernel<MODE_PUSH><<<cdiv(P, TB), TB, 0, stream>>>(0, P, t, cam, geom, reinterpret_cast<float4*>(sink), h, nog, st, counters, capacity,
+	                                                                  nullptr, dp);
+	PSB_LAUNCH_OK();
+	return 0;
+}
+
+int launch_shard_adam(const DpShard& d, const TrainTensors& t, const StepHyper& h, float grad_scale, cudaStream_t stream)
+{
+	if (d.nlocal <= 0) return 0;
+	AdamCoef ac;
+	ac.beta1 = h.beta1; ac.beta2 = h.beta2; ac.eps = h.eps; ac.inv_bc1 = h.inv_bc1; ac.inv_bc2_sqrt = 1.0f / h.bc2_sqrt;
+	shard_adam_small_kernel<<<d.nlocal, TB, 0, stream>>>(d, t, h, grad_scale);
+	PSB_LAUNCH_OK();
+	shard_adam_frest_kernel<<<d.nlocal, 256, 0, stream>>>(d, t, h.lr[2] * ac.inv_bc1, ac);
+	PSB_LAUNCH_OK();
+	return 0;
+}
+
+int launch_wait_flags(const uint32_t* flags, int world, uint32_t epoch, uint32_t* status, cudaStream_t stream)
+{
+	static const unsigned long long timeout_ns = (unsigned long long)(getenv("PSB_DP_TIMEOUT_MS") ? atoll(getenv("PSB_DP_TIMEOUT_MS")) : 20000) * 1000000ull;
+	wait_flags_kernel<<<1, 32, 0, stream>>>(flags, world, epoch, status, timeout_ns);
 	PSB_LAUNCH_OK();
 	return 0;
 }
@@ -330,8 +607,8 @@ int launch_adam(size_t n, float* p, float* m, float* v, const float* g, float lr
 		                                                             reinterpret_cast<const float4*>(g), lr, c, grad_scale);
 		PSB_LAUNCH_OK();
 	}
-	for (size_t s = n4 * 4; s < n; s += 256) {
-		adam_tail_kernel<<<1, 256, 0, stream>>>(s, n, p, m, v, g, lr, c, grad_scale);
+	if (n4 * 4 < n) {  // unaligned tensors / < 4 trailing elements: ONE scalar launch over the remainder
+		adam_tail_kernel<<<(unsigned)((n - n4 * 4 + 255) / 256), 256, 0, stream>>>(n4 * 4, n, p, m, v, g, lr, c, grad_scale);
 		PSB_LAUNCH_OK();
 	}
 	return 0;

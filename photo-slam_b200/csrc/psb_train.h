@@ -29,6 +29,36 @@ struct DensifyStats {
 	float* denom;               // [P,1]
 };
 
+// ---- NVLink data-parallel step (psb_dp_*, include/psb200.h) -----------------------------------------------------------
+// Ownership: Gaussians are cut into chunks of 128 (one block of the per-Gaussian backward); chunk c belongs to rank
+// c % world and is that rank's local chunk c / world. Every rank holds a symmetric arena (same layout, peer-mapped through
+// CUDA IPC): the six parameter tensors, an inbox [world][nlocal_max][128][20 floats], per-rank meta rows and epoch flags.
+constexpr int DP_MAX_WORLD = 8;
+constexpr int DP_REC = 20;   // floats per gradient record: g_xyz 3 | g_dc 3 | g_opacity 1 | g_scaling 3 | g_rotation 4 | masked dL/dRGB 3 | pad 2 | epoch
+struct DpPush {              // what the per-Gaussian backward needs to deliver its records
+	float* inbox[DP_MAX_WORLD];        // inbox base of every rank (own included), peer-mapped
+	float* meta[DP_MAX_WORLD];         // [world][8] floats on every rank: row r = camera centre + SH degree of rank r this step
+	uint32_t* grad_flag[DP_MAX_WORLD]; // [world] epoch words on every rank: word r = "rank r's records of this epoch have landed"
+	uint32_t* done_counter;            // local
+	int world, rank, nlocal_max;
+	uint32_t epoch;
+};
+struct DpShard {             // what the owner-side Adam kernels need
+	float* param[DP_MAX_WORLD][6];     // the six parameter tensors on every rank (row of `rank` = local)
+	uint32_t* param_flag[DP_MAX_WORLD];// [world] epoch words on every rank: word r = "rank r's updated rows have landed"
+	const float* inbox;                // local inbox
+	const float* meta;                 // local meta rows
+	float* g_rest;                     // local scratch [nlocal_max*128][45]: summed f_rest gradient of the owned rows
+	uint32_t* done_counter;            // local
+	int world, rank, nlocal_max, nlocal, P;
+	uint32_t epoch;
+};
+int launch_push_backward(int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, const StepHyper& h,
+                         const DensifyStats& st, const uint32_t* counters, uint32_t capacity, const DpPush& dp, cudaStream_t stream);
+int launch_shard_adam(const DpShard& d, const TrainTensors& t, const StepHyper& h, float grad_scale, cudaStream_t stream);
+// spins (device side, one warp) until flags[0..world) >= epoch; after `timeout_ms` writes 1 to *status and gives up
+int launch_wait_flags(const uint32_t* flags, int world, uint32_t epoch, uint32_t* status, cudaStream_t stream);
+
 // Gaussians [first, P) (first must be a multiple of 128 so f_rest chunks stay 16-byte aligned)
 // seeds: scratch [P][20] floats (per-Gaussian SH gradient seeds handed from the per-Gaussian kernel to the f_rest stream kernel)
 int launch_fused_backward(bool adam, int first, int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, float* seeds,

@@ -21,7 +21,10 @@ struct psb_trainer {
 	float* sink = nullptr; float* seeds = nullptr; size_t sink_P = 0;
 	double* sums = nullptr;      // device [2]
 	double* h_sums = nullptr;    // pinned [2]
-	uint32_t* h_count = nullptr; // pinned [1]
+	uint32_t* h_count = nullptr; // pinned [4]: instance count of the last call | sticky overflow record {count, first seq, largest count}
+	uint32_t* ovf = nullptr;     // device [4]: the sticky overflow record (tile_ranges_kernel), collected by psb_trainer_result
+	uint32_t seq = 0;            // sequence number of the last forward pass (render / step / backward) of this context
+	uint32_t ovf_first = 0, ovf_count = 0;  // what the last PSB_ERR_RETRY was about (psb_trainer_overflow_info)
 	cudaEvent_t readback = nullptr;  // recorded once the instance count (and the loss sums) of the last call are in pinned memory
 	int last_P = 0, last_W = 0, last_H = 0;
 	float last_lambda = 0.2f;
@@ -80,7 +83,11 @@ int ensure(psb_trainer* t, int P, int W, int H, cudaStream_t stream)
 	if (!t->sums) {
 		if ((rc = dev_alloc(&t->sums, 2))) return rc;
 		PSB_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&t->h_sums), 2 * sizeof(double)));
-		PSB_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&t->h_count), sizeof(uint32_t)));
+		PSB_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&t->h_count), 4 * sizeof(uint32_t)));
+		memset(t->h_count, 0, 4 * sizeof(uint32_t));
+		if ((rc = dev_alloc(&t->ovf, 4))) return rc;
+		const uint32_t init[4] = {0u, 0xFFFFFFFFu, 0u, 0u};
+		PSB_CUDA_OK(cudaMemcpy(t->ovf, init, sizeof(init), cudaMemcpyHostToDevice));
 		PSB_CUDA_OK(cudaEventCreateWithFlags(&t->readback, cudaEventDisableTiming));
 	}
 	const size_t want = (size_t)P * 6 + (1u << 16);
@@ -158,10 +165,11 @@ int forward_raw(psb_trainer* t, int P, int M, int D, const psb_model* model, con
 	t->mark(1, stream);
 	if ((rc = launch_depth_sort_and_scan(P, geom, /*scan=*/false, stream))) return rc;
 	t->mark(2, stream);
-	if ((rc = launch_scan_binning(P, cam, geom, bin, img, t->capacity, t->tight, stream))) return rc;
+	if ((rc = launch_scan_binning(P, cam, geom, bin, img, t->capacity, t->tight, t->ovf, ++t->seq, stream))) return rc;
 	t->mark(3, stream);
 	// the instance count travels to pinned memory as soon as it exists: psb_trainer_result waits on `readback`, not on the stream
 	PSB_CUDA_OK(cudaMemcpyAsync(t->h_count, geom.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	PSB_CUDA_OK(cudaMemcpyAsync(t->h_count + 1, t->ovf, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
 	PSB_CUDA_OK(cudaEventRecord(t->readback, stream));
 	const int res = make_sort_plan(tile_id_bits(cam.grid_x * cam.grid_y)).npass & 1;
 	rc = launch_render_forward(cam, img.ranges, bin.inst[res], geom.rec, background, out_color ? out_color : t->image, img.final_T,
@@ -216,7 +224,179 @@ int step_impl(psb_trainer* t, int P, int M, const psb_model* model, const psb_ca
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------------------------------
+// NVLink data-parallel context (psb_dp_*): the symmetric arena of one rank and its peer mappings.
+// ------------------------------------------------------------------------------------------------------------------------
+struct psb_dp {
+	int rank = 0, world = 1, P = 0;
+	int nchunks = 0, nlocal_max = 0, nlocal = 0;
+	char* base = nullptr;                       // local arena (cudaMalloc: exportable through CUDA IPC)
+	char* peer[DP_MAX_WORLD] = {};              // arena of every rank in this process' address space (peer[rank] == base)
+	size_t off_param[6] = {}, off_inbox = 0, off_meta = 0, off_gflag = 0, off_pflag = 0, bytes = 0;
+	float* g_rest = nullptr;                    // local scratch
+	uint32_t* local = nullptr;                  // [8]: 0 = backward done-counter, 1 = adam done-counter, 2 = status (1 = a wait timed out)
+	uint32_t epoch = 0;
+	bool connected = false;
+	cudaIpcMemHandle_t handle;
+};
+
+namespace {
+constexpr size_t DP_ROW[6] = {3, 3, 45, 1, 3, 4};
+void dp_layout(psb_dp* d)
+{
+	size_t o = 0;
+	for (int i = 0; i < 6; i++) { d->off_param[i] = o; o = align_up(o + (size_t)d->P * DP_ROW[i] * sizeof(float), 256); }
+	d->off_inbox = o; o = align_up(o + (size_t)d->world * d->nlocal_max * 128 * DP_REC * sizeof(float), 256);
+	d->off_meta = o; o += 256;
+	d->off_gflag = o; o += 256;
+	d->off_pflag = o; o += 256;
+	d->bytes = o;
+}
+}  // namespace
+
 extern "C" {
+
+int psb_dp_create(psb_dp** out, int rank, int world, int P)
+{
+	if (!out || world < 1 || world > DP_MAX_WORLD || rank < 0 || rank >= world || P < 0) { set_error_msg("psb_dp_create: need 0 <= rank < world <= 8, P >= 0"); return PSB_ERR_ARG; }
+	psb_dp* d = new psb_dp();
+	d->rank = rank; d->world = world; d->P = P;
+	d->nchunks = (P + 127) / 128;
+	d->nlocal_max = (d->nchunks + world - 1) / world;
+	d->nlocal = d->nchunks > rank ? (d->nchunks - rank + world - 1) / world : 0;
+	dp_layout(d);
+	cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d->base), d->bytes);
+	if (e == cudaSuccess) e = cudaMemset(d->base, 0, d->bytes);
+	if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d->g_rest), ((size_t)d->nlocal_max * 128 * 45 + 64) * sizeof(float));
+	if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d->local), 8 * sizeof(uint32_t));
+	if (e == cudaSuccess) e = cudaMemset(d->local, 0, 8 * sizeof(uint32_t));
+	if (e == cudaSuccess && world > 1) e = cudaIpcGetMemHandle(&d->handle, d->base);
+	if (e != cudaSuccess) {
+		set_error("psb_dp_create", e, __FILE__, __LINE__);
+		cudaFree(d->base); cudaFree(d->g_rest); cudaFree(d->local);
+		delete d;
+		return PSB_ERR_CUDA;
+	}
+	d->peer[rank] = d->base;
+	d->connected = world == 1;
+	*out = d;
+	return 0;
+}
+
+int psb_dp_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int psb_dp_ipc_handle(psb_dp* d, void* out_handle)
+{
+	if (!d || !out_handle) { set_error_msg("psb_dp_ipc_handle: null"); return PSB_ERR_ARG; }
+	memcpy(out_handle, &d->handle, sizeof(cudaIpcMemHandle_t));
+	return 0;
+}
+
+int psb_dp_connect(psb_dp* d, const void* handles)
+{
+	if (!d || (d->world > 1 && !handles)) { set_error_msg("psb_dp_connect: null"); return PSB_ERR_ARG; }
+	for (int j = 0; j < d->world; j++) {
+		if (j == d->rank || d->peer[j]) continue;
+		cudaIpcMemHandle_t h;
+		memcpy(&h, static_cast<const char*>(handles) + (size_t)j * sizeof(h), sizeof(h));
+		void* p = nullptr;
+		PSB_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+		d->peer[j] = static_cast<char*>(p);
+	}
+	d->connected = true;
+	return 0;
+}
+
+int psb_dp_params(psb_dp* d, float** out6)
+{
+	if (!d || !out6) { set_error_msg("psb_dp_params: null"); return PSB_ERR_ARG; }
+	for (int i = 0; i < 6; i++) out6[i] = reinterpret_cast<float*>(d->base + d->off_param[i]);
+	return 0;
+}
+
+int psb_dp_destroy(psb_dp* d)
+{
+	if (!d) return 0;
+	cudaDeviceSynchronize();
+	for (int j = 0; j < d->world; j++)
+		if (j != d->rank && d->peer[j]) cudaIpcCloseMemHandle(d->peer[j]);
+	cudaFree(d->base); cudaFree(d->g_rest); cudaFree(d->local);
+	delete d;
+	return 0;
+}
+
+// Enqueues a wait (device side) until every rank's parameter rows of the last psb_dp_step have landed in THIS rank's
+// tensors: after it, the local replica is complete and may be read by anything that follows on `stream`.
+int psb_dp_sync(psb_dp* d, void* stream_)
+{
+	if (!d) { set_error_msg("psb_dp_sync: null"); return PSB_ERR_ARG; }
+	if (d->epoch == 0 || d->world == 1) return 0;
+	return launch_wait_flags(reinterpret_cast<const uint32_t*>(d->base + d->off_pflag), d->world, d->epoch, d->local + 2, (cudaStream_t)stream_);
+}
+
+// 0 = healthy, 1 = a cross-rank wait timed out (a peer never arrived); synchronises the stream
+int psb_dp_status(psb_dp* d, void* stream_)
+{
+	if (!d) { set_error_msg("psb_dp_status: null"); return PSB_ERR_ARG; }
+	uint32_t st = 0;
+	PSB_CUDA_OK(cudaMemcpyAsync(&st, d->local + 2, sizeof(st), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+	PSB_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream_));
+	return (int)st;
+}
+
+int psb_dp_step(psb_trainer* t, psb_dp* d, int P, int M, const psb_model* model, const psb_camera* camera, const float* background,
+                const float* gt_image, const float* mask, const psb_step* step, float* out_color, int* radii, void* stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	int rc;
+	if (!d || !d->connected || P != d->P || !model) { set_error_msg("psb_dp_step: context not connected or built for a different P"); return PSB_ERR_ARG; }
+	if ((rc = check_model(P, M, model, true))) return rc;
+	for (int i = 0; i < 6; i++)
+		if (P > 0 && model->param[i] != reinterpret_cast<float*>(d->base + d->off_param[i])) {
+			set_error_msg("psb_dp_step: the model's parameter tensors must be the arena tensors returned by psb_dp_params");
+			return PSB_ERR_ARG;
+		}
+	const uint32_t epoch = ++d->epoch;
+	// every rank's updated rows of the previous step must have landed here before this step reads the parameters
+	if (epoch > 1 && d->world > 1)
+		if ((rc = launch_wait_flags(reinterpret_cast<const uint32_t*>(d->base + d->off_pflag), d->world, epoch - 1, d->local + 2, stream))) return rc;
+	// render, loss, tile backward (the 9 screen-space sums per Gaussian)
+	if ((rc = step_impl(t, P, M, model, camera, background, gt_image, mask, step, out_color, radii, nullptr, stream, /*tiles_only=*/true))) return rc;
+	if (P == 0) return 0;
+	char* gc = t->geom_chunk;
+	GeomState geom = GeomState::from_chunk(gc, (size_t)P);
+	const Camera cam = to_camera(camera);
+	TrainTensors tt;
+	for (int i = 0; i < 6; i++) { tt.p[i] = model->param[i]; tt.m[i] = model->exp_avg[i]; tt.v[i] = model->exp_avg_sq[i]; }
+	DensifyStats st;
+	st.enabled = (step->update_densify_stats && model->max_radii2D && model->xyz_gradient_accum && model->denom) ? 1 : 0;
+	st.max_radii2D = model->max_radii2D; st.xyz_gradient_accum = model->xyz_gradient_accum; st.denom = model->denom;
+	const StepHyper h = to_hyper(step);
+	DpPush push;
+	memset(&push, 0, sizeof(push));
+	DpShard sh;
+	memset(&sh, 0, sizeof(sh));
+	for (int j = 0; j < d->world; j++) {
+		push.inbox[j] = reinterpret_cast<float*>(d->peer[j] + d->off_inbox);
+		push.meta[j] = reinterpret_cast<float*>(d->peer[j] + d->off_meta);
+		push.grad_flag[j] = reinterpret_cast<uint32_t*>(d->peer[j] + d->off_gflag);
+		sh.param_flag[j] = reinterpret_cast<uint32_t*>(d->peer[j] + d->off_pflag);
+		for (int i = 0; i < 6; i++) sh.param[j][i] = reinterpret_cast<float*>(d->peer[j] + d->off_param[i]);
+	}
+	push.done_counter = d->local; push.world = d->world; push.rank = d->rank; push.nlocal_max = d->nlocal_max; push.epoch = epoch;
+	// per-Gaussian backward; its 80-byte records go straight into the owners' inboxes
+	if ((rc = launch_push_backward(P, tt, cam, geom, t->sink, h, st, geom.counters, (uint32_t)t->capacity, push, stream))) return rc;
+	// every rank's records of this epoch have landed here
+	if ((rc = launch_wait_flags(reinterpret_cast<const uint32_t*>(d->base + d->off_gflag), d->world, epoch, d->local + 2, stream))) return rc;
+	sh.inbox = reinterpret_cast<const float*>(d->base + d->off_inbox);
+	sh.meta = reinterpret_cast<const float*>(d->base + d->off_meta);
+	sh.g_rest = d->g_rest; sh.done_counter = d->local + 1;
+	sh.world = d->world; sh.rank = d->rank; sh.nlocal_max = d->nlocal_max; sh.nlocal = d->nlocal; sh.P = P; sh.epoch = epoch;
+	rc = launch_shard_adam(sh, tt, h, 1.0f / (float)d->world, stream);
+	t->mark(7, stream);
+	t->ev_recorded = t->profiling && t->ev_ready;
+	return rc;
+}
 
 int psb_trainer_create(psb_trainer** out)
 {
@@ -229,7 +409,8 @@ int psb_trainer_destroy(psb_trainer* t)
 {
 	if (!t) return 0;
 	cudaFree(t->geom_chunk); cudaFree(t->img_chunk); cudaFree(t->bin_chunk); cudaFree(t->image); cudaFree(t->dL_dpix); cudaFree(t->dmap);
-	cudaFree(t->sink); cudaFree(t->seeds); cudaFree(t->sums);
+	cudaFree(t->sink); cudaFree(t->seeds); cudaFree(t->sums); cudaFree(t->ovf);
+	if (t->ev_ready) for (int i = 0; i <= psb_trainer::NSTAGE; i++) cudaEventDestroy(t->ev[i]);
 	if (t->h_sums) cudaFreeHost(t->h_sums);
 	if (t->h_count) cudaFreeHost(t->h_count);
 	if (t->readback) cudaEventDestroy(t->readback);
@@ -260,6 +441,10 @@ int psb_trainer_backward(psb_trainer* t, int P, int M, const psb_model* model, c
 {
 	if (!grads) { set_error_msg("psb_trainer_backward: grads required"); return PSB_ERR_ARG; }
 	for (int i = 0; i < 6; i++) if (P > 0 && !grads[i]) { set_error_msg("psb_trainer_backward: null gradient segment"); return PSB_ERR_ARG; }
+	if (P > 0 && ((reinterpret_cast<uintptr_t>(grads[2]) | reinterpret_cast<uintptr_t>(grads[5])) & 15)) {
+		set_error_msg("psb_trainer_backward: the features_rest and rotation gradient segments must be 16-byte aligned");
+		return PSB_ERR_ARG;
+	}
 	return step_impl(t, P, M, model, camera, background, gt_image, mask, step, out_color, radii, grads, (cudaStream_t)stream_);
 }
 
@@ -277,6 +462,10 @@ int psb_trainer_backward_slab(psb_trainer* t, int P, int M, const psb_model* mod
 	if ((rc = check_model(P, M, model, false))) return rc;
 	if (first < 0 || count < 0 || first + count > P || (first % 128) != 0) { set_error_msg("psb_trainer_backward_slab: slab must start at a multiple of 128"); return PSB_ERR_ARG; }
 	if (count == 0) return 0;
+	if ((reinterpret_cast<uintptr_t>(grads[2]) | reinterpret_cast<uintptr_t>(grads[5])) & 15) {
+		set_error_msg("psb_trainer_backward_slab: the features_rest and rotation gradient blocks must be 16-byte aligned");
+		return PSB_ERR_ARG;
+	}
 	char* gc = t->geom_chunk;
 	GeomState geom = GeomState::from_chunk(gc, (size_t)P);
 	const Camera cam = to_camera(camera);
@@ -318,18 +507,27 @@ int psb_trainer_result(psb_trainer* t, float* out3, int* num_rendered, void* str
 	cudaStream_t stream = (cudaStream_t)stream_;
 	if (!t || t->geom_P < 0) { set_error_msg("psb_trainer_result: no step has run"); return PSB_ERR_ARG; }
 	PSB_CUDA_OK(cudaEventSynchronize(t->readback));
-	const uint32_t n = t->geom_P > 0 ? *t->h_count : 0;
+	const uint32_t n = t->geom_P > 0 ? t->h_count[0] : 0;
 	if (num_rendered) *num_rendered = (int)n;
-	if (n > t->capacity) {
-		// grow the binning arena; the step that just ran did not touch the parameters (its remaining kernels are no-ops,
-		// but they may still be in flight: drain the stream before the arena is replaced)
+	const uint32_t n_ovf = t->geom_P > 0 ? t->h_count[1] : 0;
+	if (n_ovf > 0) {
+		// One or more views since the last collection needed more instances than the binning arena holds: those calls were
+		// no-ops on the model (fused step) / contributed zero gradients (data-parallel modes). The record is sticky on the device,
+		// so a queued overflow is reported here even when later steps fitted. Grow the arena (the remaining kernels may still be
+		// in flight: drain first), clear the record, tell the caller which call it was.
 		PSB_CUDA_OK(cudaStreamSynchronize(stream));
 		PSB_CUDA_OK(cudaDeviceSynchronize());
-		t->capacity = (size_t)(n * 1.25) + (1u << 16);
+		uint32_t rec[3];
+		PSB_CUDA_OK(cudaMemcpy(rec, t->ovf, sizeof(rec), cudaMemcpyDeviceToHost));
+		t->ovf_count = rec[0]; t->ovf_first = rec[1];
+		const uint32_t init[4] = {0u, 0xFFFFFFFFu, 0u, 0u};
+		PSB_CUDA_OK(cudaMemcpy(t->ovf, init, sizeof(init), cudaMemcpyHostToDevice));
+		t->h_count[1] = 0;
+		t->capacity = (size_t)(rec[2] * 1.25) + (1u << 16);
 		t->bin_bytes = required_bytes<BinState>(t->capacity);
 		int rc;
 		if ((rc = dev_alloc(&t->bin_chunk, t->bin_bytes))) return rc;
-		set_error_msg("psb_trainer: binning arena was too small for this view; it has been grown, repeat the step");
+		set_error_msg("psb_trainer: binning arena was too small for a view; it has been grown, repeat the call (psb_trainer_overflow_info says which)");
 		return PSB_ERR_RETRY;
 	}
 	if (out3 && t->have_loss) {
@@ -339,6 +537,51 @@ int psb_trainer_result(psb_trainer* t, float* out3, int* num_rendered, void* str
 		out3[1] = l1;
 		out3[2] = ss;
 	}
+	return 0;
+}
+
+// Parity/debug export (tests only): per pixel, the final transmittance and the Gaussian index of the last blended splat
+// (-1: none) of the last step / render. List positions (n_contrib) are private — tight lists number the instances
+// differently from the reference — but the splat they name is comparable with the reference's
+// point_list[ranges[tile].x + n_contrib - 1] (cuda_rasterizer/forward.cu:352-365).
+__global__ void export_last_splat_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                                         const uint32_t* __restrict__ n_contrib, const float* __restrict__ final_T, int* __restrict__ last_gauss,
+                                         float* __restrict__ T_out)
+{
+	const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pix >= W * H) return;
+	const int x = pix % W, y = pix / W;
+	const uint2 r = ranges[(y / PSB_TILE_Y) * grid_x + x / PSB_TILE_X];
+	const uint32_t n = n_contrib[pix];
+	if (last_gauss) last_gauss[pix] = n ? (int)point_list[r.x + n - 1] : -1;
+	if (T_out) T_out[pix] = final_T[pix];
+}
+
+int psb_trainer_debug_state(psb_trainer* t, int width, int height, int* last_gauss, float* final_T, int* num_rendered, void* stream_)
+{
+	cudaStream_t stream = (cudaStream_t)stream_;
+	if (!t || t->geom_P < 0 || t->last_W != width || t->last_H != height) { set_error_msg("psb_trainer_debug_state: no step of that size has run"); return PSB_ERR_ARG; }
+	char* gc = t->geom_chunk; GeomState geom = GeomState::from_chunk(gc, (size_t)t->geom_P);
+	char* ic = t->img_chunk; ImgState img = ImgState::from_chunk(ic, (size_t)width * height);
+	char* bc = t->bin_chunk; BinState bin = BinState::from_chunk(bc, t->capacity);
+	const int grid_x = (width + PSB_TILE_X - 1) / PSB_TILE_X, grid_y = (height + PSB_TILE_Y - 1) / PSB_TILE_Y;
+	const int res = make_sort_plan(tile_id_bits(grid_x * grid_y)).npass & 1;
+	export_last_splat_kernel<<<(width * height + 255) / 256, 256, 0, stream>>>(width, height, grid_x, img.ranges, bin.inst[res], img.n_contrib, img.final_T,
+	                                                                        last_gauss, final_T);
+	PSB_LAUNCH_OK();
+	if (num_rendered) {
+		PSB_CUDA_OK(cudaMemcpyAsync(num_rendered, geom.counters, sizeof(int), cudaMemcpyDeviceToHost, stream));
+		PSB_CUDA_OK(cudaStreamSynchronize(stream));
+	}
+	return 0;
+}
+
+int psb_trainer_overflow_info(psb_trainer* t, unsigned* first_seq, unsigned* count, unsigned* current_seq)
+{
+	if (!t) { set_error_msg("psb_trainer_overflow_info: null"); return PSB_ERR_ARG; }
+	if (first_seq) *first_seq = t->ovf_first;
+	if (count) *count = t->ovf_count;
+	if (current_seq) *current_seq = t->seq;
 	return 0;
 }
 
@@ -372,15 +615,20 @@ int psb_loss(int height, int width, const float* image, const float* gt_image, c
 	float* dmap = nullptr;
 	double* sums = nullptr;
 	const size_t N = (size_t)height * width;
-	PSB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&dmap), 9 * N * sizeof(float)));
-	PSB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&sums), 2 * sizeof(double)));
+	// stream-ordered scratch: no device-wide synchronisation, freed on every path
+	PSB_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&dmap), 9 * N * sizeof(float), stream));
+	if (cudaMallocAsync(reinterpret_cast<void**>(&sums), 2 * sizeof(double), stream) != cudaSuccess) {
+		cudaFreeAsync(dmap, stream);
+		set_error_msg("psb_loss: out of device memory");
+		return PSB_ERR_CUDA;
+	}
 	int rc = launch_loss(height, width, image, gt_image, mask, lambda_dssim, dmap, sums, dL_dimage, stream);
 	double h[2] = {0, 0};
 	if (rc == 0) {
 		cudaMemcpyAsync(h, sums, sizeof(h), cudaMemcpyDeviceToHost, stream);
 		if (cudaStreamSynchronize(stream) != cudaSuccess) rc = PSB_ERR_CUDA;
 	}
-	cudaFree(dmap); cudaFree(sums);
+	cudaFreeAsync(dmap, stream); cudaFreeAsync(sums, stream);
 	if (rc == 0 && out3_host) {
 		const double inv_n = 1.0 / (3.0 * (double)N);
 		const float l1 = (float)(h[0] * inv_n), ss = (float)(h[1] * inv_n);

@@ -14,17 +14,44 @@ def shard_schedule(schedule, rank, world):
     return list(schedule[rank:usable:world])
 
 
+CHUNK = 128                   # Gaussians per ownership chunk of the NVLink data-parallel step (= one backward block)
+
+
+def owner_of_rows(P, world, device="cpu"):
+    """int64 [P]: rank that owns each Gaussian's optimizer state in the p2p step (psb_dp_*): chunk c = row // 128 belongs
+    to rank c % world — interleaved, so the records every rank pushes spread evenly over all NVLink destinations at any
+    moment of the backward kernel (contiguous shards would make all ranks hit the same owner at the same time)."""
+    return (torch.arange(P, device=device) // CHUNK) % world
+
+
+def gather_owned_rows(tensors, rank, world, group=None):
+    """In place: every tensor [P, ...] ends up with row r taken from the rank that owns r. Implemented as zero the rows of
+    other owners + all-reduce(SUM) — rare (before densification / a checkpoint), any backend."""
+    import torch.distributed as dist
+    if world == 1:
+        return
+    for t in tensors:
+        mine = (owner_of_rows(t.size(0), world, t.device) == rank).view(-1, *([1] * (t.dim() - 1)))
+        t.mul_(mine.to(t.dtype))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
+def _pad4(n):
+    return -(-n // 4) * 4
+
+
 class GradBuffer:
-    """ONE flat [P*59] float32 buffer with six views in the reference's tensor shapes, so the whole gradient of a
-    step is a single all-reduce call."""
+    """ONE flat float32 buffer with six views in the reference's tensor shapes, so the whole gradient of a step is a single
+    all-reduce call. Every segment starts on a 16-byte boundary (the kernels store the features_rest and rotation gradients
+    with 128-bit accesses; P need not be a multiple of 4): [P*59 (+ up to 3 pad floats per segment)]."""
 
     def __init__(self, P, device):
         self.P = P
-        self.flat = torch.zeros(P * PER_GAUSSIAN, dtype=torch.float32, device=device)
+        self.flat = torch.zeros(sum(_pad4(P * s) for s in SIZES), dtype=torch.float32, device=device)
         self.segments, o = [], 0
         for s in SIZES:
             self.segments.append(self.flat[o:o + P * s])
-            o += P * s
+            o += _pad4(P * s)
 
     def views(self):
         P = self.P
@@ -57,7 +84,6 @@ class SlabGradBuffer:
 
     def __init__(self, P, device, nslabs=4):
         self.P = P
-        self.flat = torch.zeros(max(P, 1) * PER_GAUSSIAN, dtype=torch.float32, device=device)
         per = -(-P // nslabs)
         per = -(-per // 128) * 128
         self.slabs = []           # (first, count)
@@ -65,18 +91,22 @@ class SlabGradBuffer:
         while f < P:
             self.slabs.append((f, min(per, P - f)))
             f += per
+        self.flat = torch.zeros(max(sum(self._slab_floats(c) for _, c in self.slabs), 4), dtype=torch.float32, device=device)
+
+    def _slab_floats(self, count):
+        return sum(_pad4(count * k) for k in SIZES)
 
     def region(self, s):
-        first, count = self.slabs[s]
-        return self.flat[first * PER_GAUSSIAN:(first + count) * PER_GAUSSIAN]
+        o = sum(self._slab_floats(c) for _, c in self.slabs[:s])
+        return self.flat[o:o + self._slab_floats(self.slabs[s][1])]
 
     def blocks(self, s):
-        """Six 1-D views (one per parameter tensor) of slab s."""
+        """Six 1-D views (one per parameter tensor) of slab s, each starting on a 16-byte boundary."""
         first, count = self.slabs[s]
-        out, o = [], first * PER_GAUSSIAN
+        out, o = [], sum(self._slab_floats(c) for _, c in self.slabs[:s])
         for k in SIZES:
             out.append(self.flat[o:o + count * k])
-            o += count * k
+            o += _pad4(count * k)
         return out
 
     def kernel_pointers(self, s):

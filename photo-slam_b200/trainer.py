@@ -371,16 +371,31 @@ class GaussianTrainer:
         m.step_ += 1
         self._last = (cam, gt_image, mask, out_color, radii, densify_stats)
 
+    def _overflow_info(self):
+        f, n, cur = C.c_uint(), C.c_uint(), C.c_uint()
+        self.L.psb_trainer_overflow_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+        self.L.psb_trainer_overflow_info(self.h, C.byref(f), C.byref(n), C.byref(cur))
+        return f.value, n.value, cur.value
+
     def result(self):
-        """Blocks; -> (loss, l1, ssim, num_rendered). Transparently repeats the step if the arena had to grow."""
+        """Blocks; -> (loss, l1, ssim, num_rendered). Transparently repeats the call if the binning arena had to grow for it.
+        The overflow record is sticky on the device: if an EARLIER queued step overflowed (it was a no-op on the model while
+        step_ advanced), this raises instead of silently continuing."""
         out, n = (C.c_float * 3)(), C.c_int()
         rc = self.L.psb_trainer_result(self.h, out, C.byref(n), torch.cuda.current_stream().cuda_stream)
-        if rc == -4 and getattr(self, "_last", None) is None:  # a render overflowed the arena: render again
-            cam, o, rad = self._last_render
-            self.render(cam, o, rad, check=False)
-            return self.result()
-        if rc == -4:  # PSB_ERR_RETRY: the step was a no-op
-            self.model.step_ -= 1
+        if rc == -4:
+            first, count, cur = self._overflow_info()
+            if not (count == 1 and first == cur):
+                if getattr(self, "_last", None) is not None:
+                    self.model.step_ -= count      # those updates never happened
+                    self.iteration -= count
+                raise _lib.PsbError(f"{count} queued call(s) (first: pass {first} of {cur}) overflowed the binning arena and were dropped; the arena has "
+                                    "been grown. Collect result() after every step, or render() the view once before queueing steps on it.")
+            if getattr(self, "_last", None) is None:  # a render overflowed the arena: render again
+                cam, o, rad = self._last_render
+                self.render(cam, o, rad, check=False)
+                return self.result()
+            self.model.step_ -= 1                     # PSB_ERR_RETRY: the step was a no-op
             self.iteration -= 1
             cam, gt, mask, oc, rad, ds = self._last
             self.trainForOneIteration(cam, gt, mask, oc, rad, ds)
@@ -444,22 +459,158 @@ class GaussianTrainer:
         return self.result()[0]
 
 
+class _DevArray:
+    """Zero-copy view of library-owned device memory for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2, "strides": None}
+
+
 class DataParallelTrainer(GaussianTrainer):
-    """Keyframe-sharded data parallelism: replicated Gaussians, rank r renders its own view, the flat
-    [P*59] raw-parameter gradient is summed over ranks, then every rank applies the same Adam update with
-    grad_scale = 1/world (mean over the K views of the step keeps the learning-rate scale of one view per step).
+    """Keyframe-sharded data parallelism: replicated Gaussians, rank r renders its own view, K views per
+    optimizer step (mean gradient: grad_scale = 1/world keeps the learning-rate scale of one view per step).
 
-    world == 1 (or pipeline=False): backward -> one all-reduce -> Adam.
-    world  > 1 (or pipeline=True): the per-Gaussian backward runs slab by slab; slab k is all-reduced on a side stream
-    (NCCL over NVLink) while the kernel of slab k+1 runs, and its Adam update is issued as soon as its sum has arrived."""
+    mode="p2p" (default for world > 1): the fused NVLink step of psb_dp_step — the per-Gaussian backward pushes 80-byte
+        gradient records straight into the inbox of the rank that owns the Gaussian (chunks of 128, owner = chunk % world),
+        the owner applies Adam to its rows only and stores the updated rows into every rank's parameter tensors. No reduced
+        gradient in memory, no collective call, optimizer traffic / world. The parameter tensors are re-homed in the
+        context's IPC-mapped arena; Adam moments are valid on the owner rank only (gather_moments() before densification
+        or a checkpoint).
+    mode="nccl": round-1 path kept for A/B — slab-wise backward, one NCCL all-reduce per slab on a side stream, replicated Adam.
+    world == 1 and mode=None: backward -> Adam split path on one GPU (tests)."""
 
-    def __init__(self, model, opt=None, background=None, group=None, pipeline=None, nslabs=4):
+    def __init__(self, model, opt=None, background=None, group=None, pipeline=None, nslabs=4, mode=None):
         super().__init__(model, opt, background)
+        import os
         import torch.distributed as dist
-        from .parallel import GradBuffer, SlabGradBuffer
         self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.dropped_views = 0
+        if mode is None:
+            mode = os.environ.get("PSB_DP_MODE") or ("p2p" if self.world > 1 else "nccl")
+        self.mode = mode
+        self.dp = None
+        if self.mode == "p2p":
+            try:
+                self._setup_p2p()
+                ok = 1
+            except _lib.PsbError as e:
+                self._p2p_error = str(e)
+                ok = 0
+            if self.world > 1:   # every rank must take the same path
+                t = torch.tensor([ok], device=model.device, dtype=torch.int32)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+                ok = int(t.item())
+            if not ok:
+                import warnings
+                warnings.warn("psb200: NVLink peer mapping unavailable (%s); falling back to the NCCL all-reduce path" % getattr(self, "_p2p_error", "a peer failed"))
+                self._teardown_p2p()
+                self.mode = "nccl"
+        if self.mode == "nccl":
+            self._setup_nccl(pipeline, nslabs)
+
+    # ---- p2p -----------------------------------------------------------------------------------------------------------
+    def _bind_dp(self):
+        L, vp = self.L, C.c_void_p
+        if getattr(L, "_dp_bound", False):
+            return
+        L.psb_dp_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int]
+        L.psb_dp_ipc_handle.argtypes = [vp, vp]
+        L.psb_dp_connect.argtypes = [vp, vp]
+        L.psb_dp_params.argtypes = [vp, C.POINTER(vp)]
+        L.psb_dp_step.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(_Model), C.POINTER(_Camera), vp, vp, vp, C.POINTER(_Step), vp, vp, vp]
+        L.psb_dp_sync.argtypes = [vp, vp]
+        L.psb_dp_status.argtypes = [vp, vp]
+        L.psb_dp_destroy.argtypes = [vp]
+        for n in ("psb_dp_create", "psb_dp_handle_bytes", "psb_dp_ipc_handle", "psb_dp_connect", "psb_dp_params", "psb_dp_step", "psb_dp_sync",
+                  "psb_dp_status", "psb_dp_destroy"):
+            getattr(L, n).restype = C.c_int
+        L._dp_bound = True
+
+    def _setup_p2p(self):
+        from .parallel import SIZES
+        self._bind_dp()
+        m, L = self.model, self.L
+        P = m.num_points()
+        h = C.c_void_p()
+        _lib.check(L.psb_dp_create(C.byref(h), self.rank, self.world, P), "psb_dp_create")
+        self.dp = h
+        nb = L.psb_dp_handle_bytes()
+        if self.world > 1:
+            mine = (C.c_char * nb)()
+            _lib.check(L.psb_dp_ipc_handle(h, mine), "psb_dp_ipc_handle")
+            blobs = [None] * self.world
+            self.dist.all_gather_object(blobs, bytes(mine), group=self.group)
+            allb = (C.c_char * (nb * self.world)).from_buffer_copy(b"".join(blobs))
+            _lib.check(L.psb_dp_connect(h, allb), "psb_dp_connect")
+        else:
+            _lib.check(L.psb_dp_connect(h, None), "psb_dp_connect")
+        ptrs = (C.c_void_p * 6)()
+        _lib.check(L.psb_dp_params(h, ptrs), "psb_dp_params")
+        shapes = [(P, 3), (P, 1, 3), (P, 15, 3), (P, 1), (P, 3), (P, 4)]
+        homed = []
+        for ptr, shp, src in zip(ptrs, shapes, m.tensors()):
+            t = torch.as_tensor(_DevArray(ptr, shp), device=m.device) if P > 0 else torch.empty(shp, device=m.device)
+            t.copy_(src)
+            homed.append(t)
+        self._homed = homed
+        m._set(homed)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)   # nobody pushes into an arena that is still being filled
+
+    def _teardown_p2p(self):
+        if self.dp is not None:
+            m = self.model
+            torch.cuda.synchronize()
+            if self.world > 1:
+                self.dist.barrier(group=self.group)
+            if getattr(self, "_homed", None) is not None and m.tensors()[0] is self._homed[0]:
+                m._set([t.clone() for t in m.tensors()])   # the arena is about to disappear
+            self._homed = None
+            self.L.psb_dp_destroy(self.dp)
+            self.dp = None
+
+    def close(self):
+        self._teardown_p2p()
+
+    def owner_mask(self):
+        """bool [P]: rows whose Adam moments live on this rank (chunks of 128 Gaussians, owner = chunk % world)."""
+        from .parallel import owner_of_rows
+        return owner_of_rows(self.model.num_points(), self.world, self.model.device) == self.rank
+
+    def sync(self):
+        """Device-side wait until every rank's updated rows of the last step have landed in this rank's tensors."""
+        if self.mode == "p2p":
+            _lib.check(self.L.psb_dp_sync(self.dp, torch.cuda.current_stream().cuda_stream), "psb_dp_sync")
+
+    def status(self):
+        return self.L.psb_dp_status(self.dp, torch.cuda.current_stream().cuda_stream) if self.mode == "p2p" else 0
+
+    def gather_moments(self):
+        """Every rank receives the Adam moments of all rows (they are only maintained on the owner): call before
+        densify/prune (which moves rows, hence owners) or before writing a checkpoint."""
+        if self.mode != "p2p" or self.world == 1:
+            return
+        from .parallel import gather_owned_rows
+        self.sync()
+        m = self.model
+        gather_owned_rows(m.exp_avg_ + m.exp_avg_sq_, self.rank, self.world, self.group)
+
+    def rebuild(self):
+        """After the model was resized (densify / prune / insertion): new arena, new peer mappings."""
+        if self.mode == "p2p":
+            self._teardown_p2p()
+            self._setup_p2p()
+        else:
+            self._setup_nccl(self.pipeline, len(self.grads.slabs) if self.pipeline else 4)
+
+    # ---- nccl (round-1 path) -------------------------------------------------------------------------------------------
+    def _setup_nccl(self, pipeline, nslabs):
+        from .parallel import GradBuffer, SlabGradBuffer
+        model = self.model
         self.pipeline = (self.world > 1) if pipeline is None else bool(pipeline)
         P = model.num_points()
         if self.pipeline:
@@ -492,13 +643,17 @@ class DataParallelTrainer(GaussianTrainer):
         args = (self.h, P, 16, C.byref(cm), C.byref(cc), self.background.data_ptr(), gt_image.data_ptr(),
                 mask.data_ptr() if mask is not None else None, C.byref(cs), out_color.data_ptr() if out_color is not None else None,
                 radii.data_ptr() if radii is not None else None)
-        if not self.pipeline:
+        if self.mode == "p2p":
+            _lib.check(self.L.psb_dp_step(self.h, self.dp, *args[1:], stream), "psb_dp_step")
+        elif not self.pipeline:
+            assert self.grads.P == P, "gradient buffer was built for a different model size: call rebuild() after densify/prune"
             ptrs = (C.c_void_p * 6)(*[s.data_ptr() for s in self.segs])
             _lib.check(self.L.psb_trainer_backward(*args, ptrs, stream), "psb_trainer_backward")
             scale = self.grads.all_reduce(self.group)   # ONE collective per step: 59 floats per Gaussian
             _lib.check(self.L.psb_adam_update(P, 16, C.byref(cm), ptrs, C.byref(cs), scale, stream), "psb_adam_update")
         else:
             from .parallel import SIZES
+            assert self.grads.P == P, "gradient buffer was built for a different model size: call rebuild() after densify/prune"
             _lib.check(self.L.psb_trainer_backward_begin(*args, stream), "psb_trainer_backward_begin")
             scale = 1.0 / self.world
             for s, (first, count) in enumerate(self.grads.slabs):
@@ -521,6 +676,18 @@ class DataParallelTrainer(GaussianTrainer):
                                                     C.byref(cs), scale, stream), "psb_adam_flat")
         m.step_ += 1
         self._last = (cam, gt_image, mask, out_color, radii, densify_stats)
+
+    def result(self):
+        """-> (loss, l1, ssim, num_rendered) of this rank's view. A view whose binning arena overflowed contributed a zero
+        gradient to the step (every rank still stepped, replicas identical); it is counted in `dropped_views`, the arena
+        has been grown, and the step is NOT repeated (a one-rank retry would desynchronise the group)."""
+        out, n = (C.c_float * 3)(), C.c_int()
+        rc = self.L.psb_trainer_result(self.h, out, C.byref(n), torch.cuda.current_stream().cuda_stream)
+        if rc == -4:
+            self.dropped_views += 1
+            return float("nan"), float("nan"), float("nan"), n.value
+        _lib.check(rc, "psb_trainer_result")
+        return out[0], out[1], out[2], n.value
 
     def sync_densify_stats(self):
         """Reduce the rank-local densification statistics (call right before densify/prune)."""

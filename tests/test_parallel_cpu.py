@@ -98,3 +98,43 @@ def test_two_rank_step_matches_single_process_mean_gradient():
         assert np.allclose(a, b, rtol=1e-6, atol=1e-9)
     # schedule sharding: disjoint, interleaved, K consecutive entries per step, remainder dropped
     assert res[0][1] == [0, 2, 4, 6, 8] and res[1][1] == [1, 3, 5, 7, 9]
+
+
+def _gather_worker(rank, world, port, P, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from photo_slam_b200.parallel import gather_owned_rows, owner_of_rows
+    own = owner_of_rows(P, world)
+    truth = [torch.arange(P * k, dtype=torch.float32).view(P, *sh) for k, sh in ((45, (15, 3)), (1, (1,)), (4, (4,)))]
+    mine = []
+    for t in truth:   # valid on the owned rows, garbage elsewhere (what the p2p step leaves in the moment tensors)
+        x = torch.full_like(t, float(-1000 - rank))
+        x[own == rank] = t[own == rank]
+        mine.append(x)
+    gather_owned_rows(mine, rank, world)
+    q.put((rank, all(torch.equal(a, b) for a, b in zip(mine, truth))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_owner_map_and_moment_gather_two_ranks():
+    """p2p step host logic: chunk-interleaved ownership and the gather that precedes densification / checkpoints."""
+    sys.path.insert(0, ROOT)
+    from photo_slam_b200.parallel import CHUNK, owner_of_rows
+    own = owner_of_rows(1000, 3)
+    assert CHUNK == 128 and own[0] == 0 and own[127] == 0 and own[128] == 1 and own[256] == 2 and own[384] == 0 and own[999] == (999 // 128) % 3
+    P, world = 700, 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, P, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
