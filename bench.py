@@ -52,7 +52,7 @@ def parse():
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region. In-process NVML (pynvml) every 0.2 s: spawning `nvidia-smi`
+    """SM clock / throttle reasons sampled DURING the timed region. In-process NVML (pynvml) every 20 ms: spawning `nvidia-smi`
     back to back takes driver locks and measurably slows host-bound loops (the reference arm lost 30 %), so the CLI is only
     the fallback when pynvml is unavailable."""
 
@@ -97,7 +97,7 @@ class ClockSampler:
                     self.samples.append(smp)
             except Exception:
                 pass
-            time.sleep(0.2 if self.nvml is not None else 0.5)
+            time.sleep(0.02 if self.nvml is not None else 0.5)
 
     def __enter__(self):
         self.t.start()
@@ -161,7 +161,7 @@ def make_inputs(args, rank, dev):
     return scene, cam, host, devcam, host["gt"].to(dev)
 
 
-def cpu_baseline():
+def cpu_baseline(args=None):
     """CPU restatement (oracle port, OpenMP) on a bounded sample: config A, forward + backward, no Adam."""
     import oracle_c
     W, H, fx, fy = syn.CAMERAS["tum"]
@@ -177,21 +177,31 @@ def cpu_baseline():
         oracle_c.backward(cam, act, f, dL)
         n += 1
     dt = (time.time() - t0) / n
-    return {"value": 1.0 / dt, "unit": "iters/s", "cores": cores, "kind": "port",
-            "sample": f"config A (50k Gaussians, 640x480): {n} x (forward + backward) of oracle/gs_oracle.c, OpenMP on the per-Gaussian and forward-blend loops; no loss/Adam"}
+    out = {"value": 1.0 / dt, "unit": "iters/s", "cores": cores, "kind": "port",
+           "sample": f"config A (50k Gaussians, 640x480): {n} x (forward + backward) of oracle/gs_oracle.c, OpenMP on the per-Gaussian and forward-blend loops; no loss/Adam"}
+    # north_star: "its LibTorch-CPU SH/loss path on the host cores, core count stated, as a reported baseline" — the reference's
+    # sh_utils::eval_sh (include/sh_utils.h:64-136) and loss_utils::l1_loss / ssim (include/loss_utils.h:28-124) as ATen CPU ops
+    try:
+        import ref_sh_loss_cpu
+        W, H, _, _ = syn.CAMERAS[args.camera] if args is not None else syn.CAMERAS["replica"]
+        out["libtorch_cpu_sh_loss"] = ref_sh_loss_cpu.time_sh_and_loss(min(args.points if args is not None else 500_000, 500_000), H, W, cores)
+    except Exception as e:  # reported baseline only: never fail the bench over it
+        out["libtorch_cpu_sh_loss"] = {"unavailable": repr(e)}
+    return out
 
 
-# ncu DRAM bytes per iteration of each stage at config D (profiles/r1_ncu_full_step_metrics.csv, round 1 final kernels)
-NCU_DRAM_BYTES_CONFIG_D = {"preprocess": 0.882e9, "depth_sort_scan": 0.099e9, "binning": None, "render_fwd": 0.081e9, "loss": 0.070e9,
-                           "render_bwd": 0.111e9, "backward_adam": 5.754e9}
 STAGE_KERNELS = {"preprocess": ["preprocess_fwd_kernel"], "depth_sort_scan": ["rs_histogram_kernel", "rs_scan_hist_kernel", "rs_onesweep_kernel x4"],
                  "binning": ["emit_scan_kernel", "rs_histogram_kernel", "rs_scan_hist_kernel", "rs_onesweep_kernel x2", "tile_ranges_kernel"],
                  "render_fwd": ["render_fwd_kernel"], "loss": ["loss_fwd_kernel", "loss_bwd_kernel"], "render_bwd": ["render_bwd_kernel"],
-                 "backward_adam": ["gaussian_backward_kernel", "frest_stream_kernel"]}
+                 "gaussian_backward": ["gaussian_backward_kernel"], "frest_adam": ["frest_stream_kernel"],
+                 "push_backward": ["gaussian_backward_kernel<2>"], "wait_grads": ["wait_flags_kernel"],
+                 "shard_adam": ["shard_adam_small_kernel", "shard_adam_frest_kernel"], "wait_params": ["wait_flags_kernel"]}
+SINGLE_KERNEL_STAGES = ("preprocess", "render_fwd", "render_bwd", "gaussian_backward", "frest_adam")
 
 
 def algorithmic_bytes(P, P_vis, N, W, H, T):
-    """SURVEY.md §8(d) per-unit figures x units of this workload, per stage of psb_trainer_step (bytes)."""
+    """Compulsory HBM bytes per stage of psb_trainer_step: SURVEY.md §8(d) per-unit figures x units of this workload, specialised to
+    the fused design (the gradient never exists in memory). DESIGN.md §4 states the same numbers."""
     return {
         "preprocess": 236 * P + 75 * P_vis + 8 * P,
         "depth_sort_scan": 4 * 16 * P + 8 * P,                 # 4 onesweep passes over (key,value) + offsets scan
@@ -199,8 +209,27 @@ def algorithmic_bytes(P, P_vis, N, W, H, T):
         "render_fwd": 4 * N + 48 * N + 20 * W * H + 8 * T,        # upper bound: whole list consumed
         "loss": (2 * 12 + 12) * W * H + 2 * 36 * W * H,
         "render_bwd": 4 * N + 48 * N + 20 * W * H + 36 * P_vis,
-        "backward_adam": 1652 * P + 48 * P_vis + 96 * P,          # 28 B x 59 params + screen-space sums read + sink re-zero
+        # Adam of the 14 small parameters (28 B each: read p, m, v; write p, m, v — the gradient is produced in registers) + the 9
+        # screen-space sums and the SH rows of the visible Gaussians (view-direction term of dL/dxyz) + visibility word
+        "gaussian_backward": 24 * 14 * P + (36 + 180 + 48) * P_vis + 16 * P,
+        # Adam of the [P,15,3] SH rows: read p, m, v, write p, m, v (24 B per parameter; the gradient is a product of two cached seeds)
+        "frest_adam": 24 * 45 * P,
     }
+
+
+def ncu_profile_rows():
+    """Per-kernel ncu readings of ONE training iteration of THIS round's kernels (profiles/r2_ncu_step_metrics.csv, written by
+    tools/ncu_summary.py from an `ncu --set full` capture of `bench.py --steps 2`): {kernel name prefix: row}. Empty if absent."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r2_ncu_step_metrics.csv")
+    rows = {}
+    try:
+        for r in csv.DictReader(open(path)):
+            name = r["kernel"].split("<")[0]
+            rows.setdefault(name, []).append(r)
+    except Exception:
+        pass
+    return rows
 
 
 def run_psb(args, world, rank, local, dev):
@@ -306,8 +335,28 @@ def run_psb(args, world, rank, local, dev):
     e1.record()
     torch.cuda.synchronize()
     render_ms = e0.elapsed_time(e1) / 10
-    stages, roof, stage_table = None, None, None
+    stages, roof, stage_table, dp_stages = None, None, None, None
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        peak_src = "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        pass
+    if world > 1:
+        rewind()
+        tr.set_profiling(True)
+        acc = {}
+        for _ in range(min(args.steps, 30)):
+            tr.trainForOneIteration(devcam, gt_dev)
+            tr.result()
+            for k, v in tr.stage_times().items():
+                acc.setdefault(k, []).append(v)
+        tr.set_profiling(False)
+        tr.sync()
+        barrier(world)
+        dp_stages = {k: float(np.mean(v)) for k, v in acc.items()}     # rank 0's view of one step (ms)
     if world == 1:
+        rewind()
         tr.set_profiling(True)
         acc = {}
         for _ in range(args.steps):                     # the same K iterations once more, one CUDA event per stage boundary
@@ -319,23 +368,37 @@ def run_psb(args, world, rank, local, dev):
         stages = {k: float(np.mean(v)) for k, v in acc.items()}
         T_tiles = ((W + 15) // 16) * ((H + 15) // 16)
         ab = algorithmic_bytes(P, P_vis, n_inst, W, H, T_tiles)
-        peak = 6650.0
-        peak_src = "fallback"
-        try:
-            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-            peak_src = "measured"
-        except Exception:
-            pass
-        stage_table = {k: {"ms": stages[k], "alg_GB": ab[k] / 1e9, "GBps": ab[k] / 1e6 / stages[k], "frac_of_hbm_peak": ab[k] / 1e6 / stages[k] / peak}
-                       for k in stages}
-        top = max(stages, key=stages.get)
-        roof = {"kernel": top, "bound": "hbm", "achieved": stage_table[top]["GBps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": stage_table[top]["frac_of_hbm_peak"],
-                # dram__bytes_read.sum + dram__bytes_write.sum of the stage's launches, one `ncu --set full` capture of this
-                # workload (profiles/r1_ncu_full_step_metrics.csv); null for any other workload
-                "traffic": NCU_DRAM_BYTES_CONFIG_D.get(top) if (P == 3_000_000 and args.camera == "replica") else None,
-                "launches": STAGE_KERNELS.get(top),
-                "note": "achieved = SURVEY §8(d) algorithmic bytes of the stage / its CUDA-event time inside psb_trainer_step; see stages for every stage"}
+        prof = ncu_profile_rows() if (P == 3_000_000 and args.camera == "replica") else {}
+        sm_clock_ghz = (clocks.get("sm_mhz") or 1965.0) / 1e3
+        stage_table = {}
+        for k in stages:
+            row = {"ms": stages[k], "alg_GB": ab[k] / 1e9, "GBps": ab[k] / 1e6 / stages[k], "frac_of_hbm_peak": ab[k] / 1e6 / stages[k] / peak,
+                   "kernels": STAGE_KERNELS.get(k)}
+            if k in SINGLE_KERNEL_STAGES:
+                pr = prof.get(STAGE_KERNELS[k][0])
+                if pr:   # ncu capture of the same kernels (cold-cache, serialised): DRAM traffic and warp instructions per launch
+                    row["ncu_dram_GB"] = float(pr[0]["dram_rd [Gbyte]"]) + float(pr[0]["dram_wr [Gbyte]"])
+                    row["ncu_warp_inst"] = float(pr[0]["warp_inst [inst]"])
+                    # issue roofline: warp instructions / (148 SMs x 4 schedulers x SM clock x time) — the ceiling that binds the tile kernels
+                    row["issue_frac"] = row["ncu_warp_inst"] / (148 * 4 * sm_clock_ghz * 1e9 * stages[k] * 1e-3)
+            stage_table[k] = row
+        top = max(SINGLE_KERNEL_STAGES, key=lambda k: stages[k])          # the dominant KERNEL of the step
+        top_hbm = max(("gaussian_backward", "frest_adam", "preprocess"), key=lambda k: stages[k])   # the dominant HBM-bound kernel
+        roof = {"kernel": STAGE_KERNELS[top][0], "bound": "hbm", "achieved": stage_table[top]["GBps"], "peak": peak, "peak_source": peak_src,
+                "unit": "GB/s", "frac": stage_table[top]["frac_of_hbm_peak"], "ms": stages[top],
+                "traffic": (stage_table[top].get("ncu_dram_GB") or 0) * 1e9 or None,
+                "traffic_source": "profiles/r2_ncu_step_metrics.csv (ncu --set full of this round's kernels, per launch)" if "ncu_dram_GB" in stage_table[top] else None,
+                "issue_frac": stage_table[top].get("issue_frac"),
+                "note": ("the dominant kernel of the step is the tile backward: it is ISSUE-bound (issue_frac = warp instructions / (148 SM x 4 schedulers x clock x t)); "
+                         "its HBM fraction is reported because the metric asks for it. hbm_bound_kernel = the largest kernel that IS HBM-bound.") if top in ("render_bwd", "render_fwd") else None,
+                "hbm_bound_kernel": {"kernel": STAGE_KERNELS[top_hbm][0], "ms": stages[top_hbm], "achieved": stage_table[top_hbm]["GBps"],
+                                     "frac": stage_table[top_hbm]["frac_of_hbm_peak"], "alg_GB": stage_table[top_hbm]["alg_GB"],
+                                     "traffic": (stage_table[top_hbm].get("ncu_dram_GB") or 0) * 1e9 or None},
+                "optimizer_stage": {"kernels": ["gaussian_backward_kernel", "frest_stream_kernel"], "ms": stages["gaussian_backward"] + stages["frest_adam"],
+                                    "alg_GB_fused_minimum": (ab["gaussian_backward"] + ab["frest_adam"]) / 1e9,
+                                    "alg_GB_survey_8d": (1652 * P + 559 * P_vis) / 1e9,
+                                    "frac_fused_minimum": (ab["gaussian_backward"] + ab["frest_adam"]) / 1e6 / (stages["gaussian_backward"] + stages["frest_adam"]) / peak,
+                                    "frac_survey_8d": (1652 * P + 559 * P_vis) / 1e6 / (stages["gaussian_backward"] + stages["frest_adam"]) / peak}}
 
     # kernels of this library per iteration (memsets not counted). p2p: 17 up to the tile backward + param-flag wait + push backward
     # + grad-flag wait + 2 owner-side Adam kernels; nccl: 4 slabs x (2 backward + 6 Adam)
@@ -359,6 +422,8 @@ def run_psb(args, world, rank, local, dev):
     if stage_table:
         out["stages"] = stage_table
         out["roofline"] = roof
+    if dp_stages:
+        out["dp_stages_ms_rank0"] = dp_stages
     return out
 
 
@@ -460,7 +525,7 @@ def main():
     out = run_psb(args, world, rank, local, dev)
     if rank == 0:
         if not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline()
+            out["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(out), flush=True)
     if world > 1:
         import torch.distributed as dist

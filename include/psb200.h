@@ -124,6 +124,7 @@ typedef struct psb_model {
 	float* max_radii2D;       /* [P]   or NULL */
 	float* xyz_gradient_accum;/* [P,1] or NULL */
 	float* denom;             /* [P,1] or NULL */
+	int* exist_since_iter;    /* [P] int32 or NULL (GaussianModel::exist_since_iter_; only the densify / prune / insert entry points move it) */
 } psb_model;
 
 typedef struct psb_camera {
@@ -236,9 +237,12 @@ int psb_trainer_overflow_info(psb_trainer* t, unsigned* first_seq, unsigned* cou
  * tight instance lists number their entries differently. *num_rendered (host, may be NULL) = instance count. */
 int psb_trainer_debug_state(psb_trainer* t, int width, int height, int* last_gauss, float* final_T, int* num_rendered, void* stream);
 
-/* Optional per-stage timing of psb_trainer_step with CUDA events recorded on the step's stream (bench.py uses
- * it for the roofline numbers; off by default). ms[0..6] = preprocess, depth sort + scan, binning (emit + tile
- * sort + ranges), render forward, loss forward+backward, render backward, fused per-Gaussian backward + Adam. */
+/* Optional per-stage timing with CUDA events recorded on the step's stream (bench.py uses it for the roofline numbers; off by
+ * default). psb_trainer_stage_times fills ms[0..n) (n >= 7) and returns how many stages it filled:
+ *   psb_trainer_step : 8 = preprocess, depth sort, binning (emit + tile sort + ranges), render forward, loss fwd+bwd, render
+ *                      backward, per-Gaussian backward kernel, f_rest Adam kernel;
+ *   psb_dp_step      : 10 = the first six, then push backward, wait for every rank's records, owner-side Adam, and ms[9] = the
+ *                      wait at the start of the step for the previous step's rows. */
 int psb_trainer_set_profiling(psb_trainer* t, int enable);
 int psb_trainer_stage_times(psb_trainer* t, float* ms, int n);
 
@@ -247,6 +251,50 @@ int psb_trainer_stage_times(psb_trainer* t, float* ms, int n);
  * out3_host = {loss, l1, ssim}. Synchronises the stream. */
 int psb_loss(int height, int width, const float* image, const float* gt_image, const float* mask,
              float lambda_dssim, float* dL_dimage, float* out3_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused densification. Replaces GaussianModel::densifyAndPrune and everything under it (src/gaussian_model.cpp:795-815,
+ * densifyAndClone :763-793, densifyAndSplit :716-761, prunePoints :588-642, densificationPostfix :644-714): the reference
+ * re-materialises all 59 parameters + 118 Adam moments per Gaussian four times (cat, cat, mask-index, mask-index) with a
+ * blocking .item(); here every surviving row is read once and every output row written once.
+ *   plan : evaluates the clone / split / prune predicates on the P source rows, scans them, returns counts_host[5] =
+ *          {P_new, surviving originals, clones, surviving split children PER COPY, split-selected rows}. This is the one host
+ *          round trip (the caller sizes the output tensors from P_new).
+ *   apply: writes the P_new output rows of all six parameter tensors and their moments into `dst`, in the reference's row
+ *          order [surviving originals | clones | split children copy 0 | copy 1]; new rows get zero moments; the three
+ *          statistics arrays of `dst` are zeroed (reference :709-711). Split children: xyz = R(q)(z * exp(s)) + xyz,
+ *          scaling = log(exp(s)/1.6); z = normal_samples [2 * n_split, 3] (row c * n_split + rank of the parent among the
+ *          split-selected rows, the reference's repeat({N,1}) order) or, when NULL, Philox4x32-10 + Box-Muller keyed by
+ *          (cfg.seed, cfg.offset, sample row): counter-based, identical on every data-parallel replica.
+ * workspace: psb_densify_workspace_bytes(P) device bytes, the same buffer for plan and apply.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct psb_densify_cfg {
+	float max_grad;          /* densify_grad_threshold */
+	float min_opacity;       /* prune below (reference call sites: 0.005) */
+	float extent;            /* scene extent (cameras_extent_) */
+	float percent_dense;     /* GaussianModel::percentDense() */
+	int max_screen_size;     /* != 0 enables the world-size prune (max exp(scaling) > 0.1 extent), like the reference */
+	unsigned long long seed, offset;
+} psb_densify_cfg;
+size_t psb_densify_workspace_bytes(int P);
+int psb_densify_plan(int P, const psb_model* src, const psb_densify_cfg* cfg, void* workspace, int* counts_host, void* stream);
+int psb_densify_apply(int P, const psb_model* src, const psb_model* dst, int P_new, const psb_densify_cfg* cfg, const void* workspace,
+                      const float* normal_samples, void* stream);
+/* GaussianModel::prunePoints (src/gaussian_model.cpp:588-642) through the same machinery: plan from a byte mask (!= 0 = remove),
+ * counts_host as above (only [0] and [1] non-zero), then psb_densify_apply with the same workspace compacts parameters, moments
+ * and exist_since_iter; NOTE: like every densify apply it zeroes dst's statistics — pass keep_stats != 0 to compact them instead
+ * (prunePoints keeps them, :637-641). */
+int psb_prune_plan(int P, const unsigned char* mask, void* workspace, int* counts_host, void* stream);
+int psb_prune_apply(int P, const psb_model* src, const psb_model* dst, int P_new, const void* workspace, int keep_stats, void* stream);
+/* GaussianModel::increasePcd (src/gaussian_model.cpp:193-377, both overloads) minus the k-NN call: dst (P + n rows) = src rows
+ * followed by n new Gaussians: xyz = points, features_dc = RGB2SH(colors) (include/sh_utils.h:138-141), features_rest = 0,
+ * opacity = inverse_sigmoid(0.1), scaling = log(sqrt(max(dist2, 1e-7))) on all three axes (dist2 = psb_dist_cuda2 of the NEW
+ * points), rotation = (1,0,0,0), zero moments, exist_since_iter = iteration; statistics of all rows reset to zero
+ * (densificationPostfix :709-711). points/colors [n,3], dist2 [n]: device. */
+int psb_insert_points(int P, const psb_model* src, const psb_model* dst, int n, const float* points, const float* colors,
+                      const float* dist2, int iteration, void* stream);
+/* GaussianModel::resetOpacity (src/gaussian_model.cpp:556-565, incl. its no-op clamp) + zeroed opacity moments, in place. */
+int psb_reset_opacity(int P, float* opacity, float* exp_avg, float* exp_avg_sq, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Point-cloud helpers exported by the same shared objects in the reference.

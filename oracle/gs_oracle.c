@@ -755,4 +755,175 @@ void orc_scale_transform_points(int P, float scale, const float* pts, const floa
 	}
 }
 
-int orc_version(void) { return 1; }
+
+/* ---------------- densification: GaussianModel::densifyAndPrune restated STEP BY STEP in the reference's own order
+ * (src/gaussian_model.cpp:795-815 driver; :763-793 densifyAndClone; :716-761 densifyAndSplit; :644-714 densificationPostfix;
+ * :588-642 prunePoints) — deliberately NOT the fused composition the CUDA kernel uses: each step re-materialises the model
+ * like the reference's cat / mask-index chain, so the kernel's single-pass row bookkeeping is checked against an independent
+ * derivation. The random draw at::normal(means, stds) (:734) is injected: samples = 0 + stds * z with z [2*n_split, 3]
+ * supplied by the caller in the reference's repeat({N,1}) row order. Row widths: xyz 3 | f_dc 3 | f_rest 45 | opacity 1 |
+ * scaling 3 | rotation 4. Pinned against the ATen ops the reference calls by tests/test_oracle_cpu.py (oracle/ref_densify.py). */
+static const int DN_K[6] = {3, 3, 45, 1, 3, 4};
+typedef struct { int n; float* t[18]; float *accum, *denom, *maxr; } dn_model;   /* t[0..5] params, [6..11] exp_avg, [12..17] exp_avg_sq */
+
+static void dn_free(dn_model* a) { for (int i = 0; i < 18; i++) free(a->t[i]); free(a->accum); free(a->denom); free(a->maxr); }
+static float dn_smax(const float* s3) { float a = expf(s3[0]), b = expf(s3[1]), c = expf(s3[2]); float m = a > b ? a : b; return m > c ? m : c; }
+
+/* densificationPostfix (:644-714): parameters cat'ed, moments cat'ed with zeros, the three statistics RESET to zeros */
+static void dn_postfix(dn_model* a, int n_new, float* const* ext /* 6 tensors of n_new rows */)
+{
+	for (int g = 0; g < 6; g++) {
+		const int k = DN_K[g];
+		for (int part = 0; part < 3; part++) {
+			float* nt = (float*)calloc((size_t)(a->n + n_new) * k + 1, sizeof(float));
+			memcpy(nt, a->t[6 * part + g], (size_t)a->n * k * sizeof(float));
+			if (part == 0 && n_new) memcpy(nt + (size_t)a->n * k, ext[g], (size_t)n_new * k * sizeof(float));
+			free(a->t[6 * part + g]);
+			a->t[6 * part + g] = nt;
+		}
+	}
+	a->n += n_new;
+	free(a->accum); free(a->denom); free(a->maxr);
+	a->accum = (float*)calloc((size_t)a->n + 1, sizeof(float));
+	a->denom = (float*)calloc((size_t)a->n + 1, sizeof(float));
+	a->maxr = (float*)calloc((size_t)a->n + 1, sizeof(float));
+}
+/* prunePoints (:588-642): every tensor, both moments and the statistics indexed by ~mask */
+static void dn_prune(dn_model* a, const uint8_t* mask)
+{
+	int keep = 0;
+	for (int i = 0; i < a->n; i++) keep += !mask[i];
+	for (int ti = 0; ti < 18; ti++) {
+		const int k = DN_K[ti % 6];
+		float* nt = (float*)calloc((size_t)keep * k + 1, sizeof(float));
+		int d = 0;
+		for (int i = 0; i < a->n; i++) if (!mask[i]) { memcpy(nt + (size_t)d * k, a->t[ti] + (size_t)i * k, k * sizeof(float)); d++; }
+		free(a->t[ti]); a->t[ti] = nt;
+	}
+	float* st[3] = {a->accum, a->denom, a->maxr};
+	for (int q = 0; q < 3; q++) { int d = 0; for (int i = 0; i < a->n; i++) if (!mask[i]) st[q][d++] = st[q][i]; }
+	a->n = keep;
+}
+
+/* number of rows densifyAndSplit selects (the caller needs it to draw z [2*n_split, 3]) */
+int orc_densify_split_count(int P, const float* scaling, const float* accum, const float* denom, float max_grad, float extent, float percent_dense)
+{
+	int n = 0;
+	for (int i = 0; i < P; i++) {
+		float g = accum[i] / denom[i];
+		if (isnan(g)) g = 0.0f;
+		if (g >= max_grad && dn_smax(scaling + 3 * i) > percent_dense * extent) n++;
+	}
+	return n;
+}
+
+/* in: 18 tensors of P rows + statistics; out: 18 tensors with room for 2*P rows each; returns the new row count */
+int orc_densify_and_prune(int P, const float* const* in18, const float* accum, const float* denom, const float* max_radii2D,
+                          float max_grad, float min_opacity, float extent, float percent_dense, int max_screen_size,
+                          const float* z, float* const* out18)
+{
+	dn_model a;
+	a.n = P;
+	for (int ti = 0; ti < 18; ti++) {
+		const size_t bytes = (size_t)P * DN_K[ti % 6] * sizeof(float);
+		a.t[ti] = (float*)malloc(bytes + 4); memcpy(a.t[ti], in18[ti], bytes);
+	}
+	a.accum = (float*)malloc((size_t)P * 4 + 4); memcpy(a.accum, accum, (size_t)P * 4);
+	a.denom = (float*)malloc((size_t)P * 4 + 4); memcpy(a.denom, denom, (size_t)P * 4);
+	a.maxr = (float*)malloc((size_t)P * 4 + 4); memcpy(a.maxr, max_radii2D, (size_t)P * 4);
+	/* :801-802  grads = xyz_gradient_accum / denom; grads[isnan] = 0 */
+	float* grads = (float*)malloc((size_t)P * 4 + 4);
+	for (int i = 0; i < P; i++) { float g = a.accum[i] / a.denom[i]; grads[i] = isnan(g) ? 0.0f : g; }
+
+	/* ---- densifyAndClone (:763-793) */
+	{
+		uint8_t* sel = (uint8_t*)calloc((size_t)a.n + 1, 1);
+		int n_new = 0;
+		for (int i = 0; i < a.n; i++) {
+			sel[i] = sqrtf(grads[i] * grads[i]) >= max_grad && dn_smax(a.t[4] + 3 * i) <= percent_dense * extent;  /* frobenius_norm over the size-1 dim */
+			n_new += sel[i];
+		}
+		float* ext[6];
+		for (int g = 0; g < 6; g++) {
+			ext[g] = (float*)malloc((size_t)n_new * DN_K[g] * 4 + 4);
+			int d = 0;
+			for (int i = 0; i < a.n; i++) if (sel[i]) { memcpy(ext[g] + (size_t)d * DN_K[g], a.t[g] + (size_t)i * DN_K[g], DN_K[g] * 4); d++; }
+		}
+		dn_postfix(&a, n_new, ext);
+		for (int g = 0; g < 6; g++) free(ext[g]);
+		free(sel);
+	}
+	/* ---- densifyAndSplit (:716-761), N = 2 */
+	{
+		const int N = 2, n_init = a.n;
+		uint8_t* sel = (uint8_t*)calloc((size_t)n_init + 1, 1);
+		int ns = 0;
+		for (int i = 0; i < n_init; i++) {
+			const float pg = i < P ? grads[i] : 0.0f;     /* padded_grad: zeros beyond grads.size(0) */
+			sel[i] = pg >= max_grad && dn_smax(a.t[4] + 3 * i) > percent_dense * extent;
+			ns += sel[i];
+		}
+		float* ext[6];
+		for (int g = 0; g < 6; g++) ext[g] = (float*)malloc((size_t)N * ns * DN_K[g] * 4 + 4);
+		const float inv = 1.0f / (float)(0.8 * N);        /* ATen divides by a CPU scalar through its reciprocal */
+		for (int c = 0; c < N; c++) {
+			int d = 0;
+			for (int i = 0; i < n_init; i++) if (sel[i]) {
+				const int j = c * ns + d;                 /* repeat({N,1}): copy-major */
+				const float* q = a.t[5] + 4 * i;          /* build_rotation (include/general_utils.h:31-56) on the RAW rotation */
+				const float nr = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+				const float r = q[0] / nr, x = q[1] / nr, y = q[2] / nr, zq = q[3] / nr;
+				const float R[9] = {1 - 2 * (y * y + zq * zq), 2 * (x * y - r * zq), 2 * (x * zq + r * y),
+				                    2 * (x * y + r * zq), 1 - 2 * (x * x + zq * zq), 2 * (y * zq - r * x),
+				                    2 * (x * zq - r * y), 2 * (y * zq + r * x), 1 - 2 * (x * x + y * y)};
+				float smp[3];
+				for (int k = 0; k < 3; k++) smp[k] = 0.0f + expf(a.t[4][3 * i + k]) * z[3 * j + k];   /* at::normal(means, stds) with injected z */
+				for (int k = 0; k < 3; k++)
+					ext[0][3 * j + k] = R[3 * k] * smp[0] + R[3 * k + 1] * smp[1] + R[3 * k + 2] * smp[2] + a.t[0][3 * i + k];   /* bmm + xyz */
+				for (int k = 0; k < 3; k++) ext[4][3 * j + k] = logf(expf(a.t[4][3 * i + k]) * inv);
+				memcpy(ext[1] + 3 * j, a.t[1] + 3 * i, 12);
+				memcpy(ext[2] + 45 * (size_t)j, a.t[2] + 45 * (size_t)i, 180);
+				ext[3][j] = a.t[3][i];
+				memcpy(ext[5] + 4 * j, a.t[5] + 4 * i, 16);
+				d++;
+			}
+		}
+		dn_postfix(&a, N * ns, ext);
+		for (int g = 0; g < 6; g++) free(ext[g]);
+		uint8_t* filt = (uint8_t*)calloc((size_t)a.n + 1, 1);   /* cat(selected_pts_mask, zeros(N * n_sel)) */
+		memcpy(filt, sel, n_init);
+		dn_prune(&a, filt);
+		free(filt); free(sel);
+	}
+	/* ---- final prune (:806-812) */
+	{
+		uint8_t* mask = (uint8_t*)calloc((size_t)a.n + 1, 1);
+		for (int i = 0; i < a.n; i++) {
+			mask[i] = (1.0f / (1.0f + expf(-a.t[3][i]))) < min_opacity;
+			if (max_screen_size) {
+				const int big_vs = a.maxr[i] > (float)max_screen_size;          /* never true: postfix zeroed max_radii2D_ (:711) */
+				const int big_ws = dn_smax(a.t[4] + 3 * i) > 0.1f * extent;
+				mask[i] = mask[i] || big_vs || big_ws;
+			}
+		}
+		dn_prune(&a, mask);
+		free(mask);
+	}
+	for (int ti = 0; ti < 18; ti++) memcpy(out18[ti], a.t[ti], (size_t)a.n * DN_K[ti % 6] * sizeof(float));
+	const int n = a.n;
+	free(grads);
+	dn_free(&a);
+	return n;
+}
+
+/* resetOpacity (:556-565): inverse_sigmoid(min(sigmoid(o), ones_like(sigmoid(o) * 0.01))) — the clamp is a no-op (quirk 9) */
+void orc_reset_opacity(int P, float* opacity)
+{
+	for (int i = 0; i < P; i++) {
+		float a = 1.0f / (1.0f + expf(-opacity[i]));
+		if (a > 1.0f) a = 1.0f;
+		opacity[i] = logf(a / (1.0f - a));
+	}
+}
+
+int orc_version(void) { return 2; }

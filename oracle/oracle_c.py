@@ -154,3 +154,37 @@ def knn_mean_dist2(pts):
     out = np.zeros(pts.shape[0], np.float32)
     L.orc_knn_mean_dist2(C.c_int(pts.shape[0]), _p(pts), _p(out))
     return out
+
+
+DN_K = (3, 3, 45, 1, 3, 4)
+
+
+def densify_split_count(scaling, accum, denom, max_grad, extent, percent_dense):
+    L = lib()
+    L.orc_densify_split_count.restype = C.c_int
+    P = scaling.shape[0]
+    return L.orc_densify_split_count(C.c_int(P), _p(scaling), _p(accum), _p(denom), C.c_float(max_grad), C.c_float(extent), C.c_float(percent_dense))
+
+
+def densify_and_prune(p, m, v, accum, denom, max_radii, max_grad, min_opacity, extent, max_screen_size, percent_dense, z):
+    """p/m/v: lists of 6 float32 arrays [P, ...] (reference shapes). Returns (p, m, v) lists of the densified model."""
+    L = lib()
+    L.orc_densify_and_prune.restype = C.c_int
+    P = p[0].shape[0]
+    ins = [np.ascontiguousarray(a, np.float32) for a in list(p) + list(m) + list(v)]
+    outs = [np.zeros((2 * P + 1) * DN_K[i % 6], np.float32) for i in range(18)]
+    in_ptrs = (C.c_void_p * 18)(*[a.ctypes.data for a in ins])
+    out_ptrs = (C.c_void_p * 18)(*[a.ctypes.data for a in outs])
+    zz = np.ascontiguousarray(z, np.float32) if z is not None and len(z) else np.zeros((1, 3), np.float32)
+    n = L.orc_densify_and_prune(C.c_int(P), in_ptrs, _p(accum), _p(denom), _p(max_radii), C.c_float(max_grad), C.c_float(min_opacity),
+                                C.c_float(extent), C.c_float(percent_dense), C.c_int(int(max_screen_size)), _p(zz), out_ptrs)
+    shapes = [(n, 3), (n, 1, 3), (n, 15, 3), (n, 1), (n, 3), (n, 4)]
+    res = [o[:n * DN_K[i % 6]].reshape(shapes[i % 6]).copy() for i, o in enumerate(outs)]
+    return res[0:6], res[6:12], res[12:18]
+
+
+def reset_opacity(opacity):
+    L = lib()
+    o = np.ascontiguousarray(opacity, np.float32).copy()
+    L.orc_reset_opacity(C.c_int(o.size), _p(o))
+    return o

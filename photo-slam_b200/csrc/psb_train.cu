@@ -540,7 +540,7 @@ __global__ void wait_flags_kernel(const uint32_t* flags, int world, uint32_t epo
 
 int launch_fused_backward(bool adam, int first, int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, float* seeds,
                           const StepHyper& h, const GradSegments& grads, const DensifyStats& st, const uint32_t* counters, uint32_t capacity,
-                          cudaStream_t stream)
+                          cudaStream_t stream, cudaEvent_t between)
 {
 	if (P - first <= 0) return 0;
 	const int grid = cdiv(P - first, TB);
@@ -553,6 +553,7 @@ int launch_fused_backward(bool adam, int first, int P, const TrainTensors& t, co
 	if (adam) gaussian_backward_kernel<MODE_ADAM><<<grid, TB, 0, stream>>>(first, P, t, cam, geom, sink4, h, grads, st, counters, capacity, sd4, nodp);
 	else gaussian_backward_kernel<MODE_GRADS><<<grid, TB, 0, stream>>>(first, P, t, cam, geom, sink4, h, grads, st, counters, capacity, sd4, nodp);
 	PSB_LAUNCH_OK();
+	if (between) cudaEventRecord(between, stream);
 	AdamCoef ac;
 	ac.beta1 = h.beta1; ac.beta2 = h.beta2; ac.eps = h.eps; ac.inv_bc1 = h.inv_bc1; ac.inv_bc2_sqrt = 1.0f / h.bc2_sqrt;
 	const uint32_t e0 = (uint32_t)first * REST, e1 = (uint32_t)P * REST;

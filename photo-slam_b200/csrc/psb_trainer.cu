@@ -34,7 +34,12 @@ struct psb_trainer {
 	bool tight = !(getenv("PSB_TIGHT") && atoi(getenv("PSB_TIGHT")) == 0);
 	// optional per-stage timing (CUDA events on the step's stream)
 	bool profiling = false;
-	static constexpr int NSTAGE = 8;
+	// stage boundaries: 0 start | 1 preprocess | 2 depth sort | 3 binning | 4 render fwd | 5 loss | 6 render bwd |
+	//   fused step:        7 per-Gaussian backward kernel | 8 f_rest Adam stream kernel
+	//   data-parallel step: 7 push backward | 8 wait for every rank's records | 9 owner-side Adam (+ stores to every replica);
+	//                       ev[NSTAGE] is recorded BEFORE the wait for the previous step's rows (stage "wait_params" = ev[NSTAGE] -> ev[0])
+	static constexpr int NSTAGE = 10;
+	int last_stage = 0;  // index of the last boundary the last profiled call recorded
 	cudaEvent_t ev[NSTAGE + 1] = {};
 	bool ev_ready = false, ev_recorded = false;
 	void mark(int i, cudaStream_t s) { if (profiling && ev_ready) cudaEventRecord(ev[i], s); }
@@ -216,8 +221,10 @@ int step_impl(psb_trainer* t, int P, int M, const psb_model* model, const psb_ca
 	st.enabled = (step->update_densify_stats && model->max_radii2D && model->xyz_gradient_accum && model->denom) ? 1 : 0;
 	st.max_radii2D = model->max_radii2D; st.xyz_gradient_accum = model->xyz_gradient_accum; st.denom = model->denom;
 	const StepHyper h = to_hyper(step);
-	rc = launch_fused_backward(grads == nullptr, 0, P, tt, cam, geom, t->sink, t->seeds, h, gs, st, geom.counters, (uint32_t)t->capacity, stream);
-	t->mark(7, stream);
+	rc = launch_fused_backward(grads == nullptr, 0, P, tt, cam, geom, t->sink, t->seeds, h, gs, st, geom.counters, (uint32_t)t->capacity, stream,
+	                           (t->profiling && t->ev_ready) ? t->ev[7] : nullptr);
+	t->mark(8, stream);
+	t->last_stage = 8;
 	t->ev_recorded = t->profiling && t->ev_ready;
 	return rc;
 }
@@ -357,6 +364,7 @@ int psb_dp_step(psb_trainer* t, psb_dp* d, int P, int M, const psb_model* model,
 			return PSB_ERR_ARG;
 		}
 	const uint32_t epoch = ++d->epoch;
+	t->mark(psb_trainer::NSTAGE, stream);
 	// every rank's updated rows of the previous step must have landed here before this step reads the parameters
 	if (epoch > 1 && d->world > 1)
 		if ((rc = launch_wait_flags(reinterpret_cast<const uint32_t*>(d->base + d->off_pflag), d->world, epoch - 1, d->local + 2, stream))) return rc;
@@ -386,14 +394,17 @@ int psb_dp_step(psb_trainer* t, psb_dp* d, int P, int M, const psb_model* model,
 	push.done_counter = d->local; push.world = d->world; push.rank = d->rank; push.nlocal_max = d->nlocal_max; push.epoch = epoch;
 	// per-Gaussian backward; its 80-byte records go straight into the owners' inboxes
 	if ((rc = launch_push_backward(P, tt, cam, geom, t->sink, h, st, geom.counters, (uint32_t)t->capacity, push, stream))) return rc;
+	t->mark(7, stream);
 	// every rank's records of this epoch have landed here
 	if ((rc = launch_wait_flags(reinterpret_cast<const uint32_t*>(d->base + d->off_gflag), d->world, epoch, d->local + 2, stream))) return rc;
+	t->mark(8, stream);
 	sh.inbox = reinterpret_cast<const float*>(d->base + d->off_inbox);
 	sh.meta = reinterpret_cast<const float*>(d->base + d->off_meta);
 	sh.g_rest = d->g_rest; sh.done_counter = d->local + 1;
 	sh.world = d->world; sh.rank = d->rank; sh.nlocal_max = d->nlocal_max; sh.nlocal = d->nlocal; sh.P = P; sh.epoch = epoch;
 	rc = launch_shard_adam(sh, tt, h, 1.0f / (float)d->world, stream);
-	t->mark(7, stream);
+	t->mark(9, stream);
+	t->last_stage = 9;
 	t->ev_recorded = t->profiling && t->ev_ready;
 	return rc;
 }
@@ -597,14 +608,20 @@ int psb_trainer_set_profiling(psb_trainer* t, int enable)
 	return 0;
 }
 
-// ms[0..6]: preprocess, depth sort + scan, binning (emit + tile sort + ranges), render forward, loss fwd+bwd,
-// render backward, fused per-Gaussian backward + Adam — of the last profiled psb_trainer_step. Synchronises.
+// ms[i] = time between stage boundaries i and i+1 of the last profiled step (see psb_trainer::ev), i < n; entries beyond the last
+// recorded boundary are 0. Fused step: 8 stages (preprocess, depth sort, binning, render fwd, loss, render bwd, per-Gaussian
+// backward kernel, f_rest Adam kernel). Data-parallel step: 9 stages (..., render bwd, push backward, wait for the ranks' records,
+// owner-side Adam) and ms[9] = the wait for the previous step's rows at the start of the step. Synchronises. Returns the number of
+// stages filled.
 int psb_trainer_stage_times(psb_trainer* t, float* ms, int n)
 {
 	if (!t || !ms || n < 7 || !t->ev_recorded) { set_error_msg("psb_trainer_stage_times: no profiled step"); return PSB_ERR_ARG; }
-	PSB_CUDA_OK(cudaEventSynchronize(t->ev[7]));
-	for (int i = 0; i < 7; i++) PSB_CUDA_OK(cudaEventElapsedTime(&ms[i], t->ev[i], t->ev[i + 1]));
-	return 0;
+	PSB_CUDA_OK(cudaEventSynchronize(t->ev[t->last_stage]));
+	for (int i = 0; i < n; i++) ms[i] = 0.f;
+	int filled = 0;
+	for (int i = 0; i < t->last_stage && i < n; i++, filled++) PSB_CUDA_OK(cudaEventElapsedTime(&ms[i], t->ev[i], t->ev[i + 1]));
+	if (t->last_stage == 9 && n > 9) { PSB_CUDA_OK(cudaEventElapsedTime(&ms[9], t->ev[psb_trainer::NSTAGE], t->ev[0])); filled = 10; }
+	return filled;
 }
 
 int psb_loss(int height, int width, const float* image, const float* gt_image, const float* mask, float lambda_dssim, float* dL_dimage,

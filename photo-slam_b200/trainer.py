@@ -23,7 +23,7 @@ GROUPS = ("xyz", "features_dc", "features_rest", "opacity", "scaling", "rotation
 
 class _Model(C.Structure):
     _fields_ = [("param", C.c_void_p * 6), ("exp_avg", C.c_void_p * 6), ("exp_avg_sq", C.c_void_p * 6),
-                ("max_radii2D", C.c_void_p), ("xyz_gradient_accum", C.c_void_p), ("denom", C.c_void_p)]
+                ("max_radii2D", C.c_void_p), ("xyz_gradient_accum", C.c_void_p), ("denom", C.c_void_p), ("exist_since_iter", C.c_void_p)]
 
 
 class _Camera(C.Structure):
@@ -34,6 +34,11 @@ class _Camera(C.Structure):
 class _Step(C.Structure):
     _fields_ = [("lr", C.c_float * 6), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("step", C.c_int),
                 ("lambda_dssim", C.c_float), ("sh_degree", C.c_int), ("update_densify_stats", C.c_int)]
+
+
+class _DensifyCfg(C.Structure):
+    _fields_ = [("max_grad", C.c_float), ("min_opacity", C.c_float), ("extent", C.c_float), ("percent_dense", C.c_float), ("max_screen_size", C.c_int),
+                ("seed", C.c_ulonglong), ("offset", C.c_ulonglong)]
 
 
 def _bind():
@@ -52,6 +57,16 @@ def _bind():
     L.psb_loss.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_float, vp, C.POINTER(C.c_float), vp]
     for n in ("psb_trainer_create", "psb_trainer_destroy", "psb_trainer_render", "psb_trainer_step", "psb_trainer_backward",
               "psb_adam_update", "psb_trainer_result", "psb_loss"):
+        getattr(L, n).restype = C.c_int
+    L.psb_densify_workspace_bytes.argtypes = [C.c_int]
+    L.psb_densify_workspace_bytes.restype = C.c_size_t
+    L.psb_densify_plan.argtypes = [C.c_int, C.POINTER(_Model), C.POINTER(_DensifyCfg), vp, C.POINTER(C.c_int), vp]
+    L.psb_densify_apply.argtypes = [C.c_int, C.POINTER(_Model), C.POINTER(_Model), C.c_int, C.POINTER(_DensifyCfg), vp, vp, vp]
+    L.psb_prune_plan.argtypes = [C.c_int, vp, vp, C.POINTER(C.c_int), vp]
+    L.psb_prune_apply.argtypes = [C.c_int, C.POINTER(_Model), C.POINTER(_Model), C.c_int, vp, C.c_int, vp]
+    L.psb_insert_points.argtypes = [C.c_int, C.POINTER(_Model), C.POINTER(_Model), C.c_int, vp, vp, vp, C.c_int, vp]
+    L.psb_reset_opacity.argtypes = [C.c_int, vp, vp, vp, vp]
+    for n in ("psb_densify_plan", "psb_densify_apply", "psb_prune_plan", "psb_prune_apply", "psb_insert_points", "psb_reset_opacity"):
         getattr(L, n).restype = C.c_int
     L._trainer_bound = True
     return L
@@ -183,9 +198,10 @@ class GaussianModel:
             self.active_sh_degree_ += 1
 
     # ------------------------------------------------------------------------------------------------------------
-    # Densification / pruning / insertion. These are NOT on the per-iteration hot path (every 100 iterations /
-    # per keyframe); like the reference they are tensor surgery with framework ops on the device, mirrored call for
-    # call, on this model's tensors and Adam moments (the reference edits torch::optim::Adam's state in place).
+    # Densification / pruning / insertion / loop-closure surgery (reference src/gaussian_model.cpp:193-475, 556-815).
+    # Every one of them is a fused device pass over the model through the C-ABI (psb_densify_* / psb_prune_* /
+    # psb_insert_points / psb_reset_opacity): one read of the surviving rows, one write of the output rows, one host
+    # round trip (the new row count). The ATen restatement of the reference code lives in oracle/ref_densify.py (tests only).
     # ------------------------------------------------------------------------------------------------------------
     def getOpacityActivation(self): return torch.sigmoid(self.opacity_)
     def getScalingActivation(self): return torch.exp(self.scaling_)
@@ -194,97 +210,151 @@ class GaussianModel:
     def _set(self, tensors):
         (self.xyz_, self.features_dc_, self.features_rest_, self.opacity_, self.scaling_, self.rotation_) = tensors
 
+    def _exist(self):
+        if getattr(self, "exist_since_iter_", None) is None or self.exist_since_iter_.size(0) != self.num_points():
+            self.exist_since_iter_ = torch.zeros(self.num_points(), dtype=torch.int32, device=self.device)
+        return self.exist_since_iter_
+
+    def _blank(self, P):
+        """Uninitialised tensors of a P-row model (parameters, both moments, statistics, exist_since_iter)."""
+        M = (self.max_sh_degree_ + 1) ** 2
+        shapes = [(P, 3), (P, 1, 3), (P, M - 1, 3), (P, 1), (P, 3), (P, 4)]
+        e = lambda sh: torch.empty(sh, dtype=torch.float32, device=self.device)
+        return dict(p=[e(sh) for sh in shapes], m=[e(sh) for sh in shapes], v=[e(sh) for sh in shapes], accum=e((P, 1)), denom=e((P, 1)),
+                    max_radii=e((P,)), exist=torch.empty(P, dtype=torch.int32, device=self.device))
+
+    @staticmethod
+    def _cm(p, m, v, accum, denom, max_radii, exist):
+        c = _Model()
+        for i in range(6):
+            c.param[i], c.exp_avg[i], c.exp_avg_sq[i] = p[i].data_ptr(), m[i].data_ptr(), v[i].data_ptr()
+        c.max_radii2D, c.xyz_gradient_accum, c.denom, c.exist_since_iter = max_radii.data_ptr(), accum.data_ptr(), denom.data_ptr(), exist.data_ptr()
+        return c
+
+    def _src(self):
+        self._exist()
+        return self._cm(self.tensors(), self.exp_avg_, self.exp_avg_sq_, self.xyz_gradient_accum_, self.denom_, self.max_radii2D_, self.exist_since_iter_)
+
+    def _adopt(self, d):
+        self._set(d["p"])
+        self.exp_avg_, self.exp_avg_sq_ = d["m"], d["v"]
+        self.xyz_gradient_accum_, self.denom_, self.max_radii2D_, self.exist_since_iter_ = d["accum"], d["denom"], d["max_radii"], d["exist"]
+
     def resetOpacity(self):
         """reference gaussian_model.cpp:556-565. NOTE: the reference's misplaced parenthesis makes this
         min(sigmoid(o), 1) — it does NOT clamp to 0.01; only the opacity moments are zeroed."""
-        act = self.getOpacityActivation()
-        new = torch.min(act, torch.ones_like(act * 0.01))
-        self.opacity_ = torch.log(new / (1 - new)).contiguous()      # inverse_sigmoid
-        self.exp_avg_[3] = torch.zeros_like(self.opacity_)
-        self.exp_avg_sq_[3] = torch.zeros_like(self.opacity_)
+        L = _bind()
+        _lib.check(L.psb_reset_opacity(self.num_points(), self.opacity_.data_ptr(), self.exp_avg_[3].data_ptr(), self.exp_avg_sq_[3].data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream), "psb_reset_opacity")
 
     def prunePoints(self, mask):
-        """reference gaussian_model.cpp:588-642"""
-        valid = ~mask
-        self._set([t[valid].contiguous() for t in self.tensors()])
-        self.exp_avg_ = [t[valid].contiguous() for t in self.exp_avg_]
-        self.exp_avg_sq_ = [t[valid].contiguous() for t in self.exp_avg_sq_]
-        self.xyz_gradient_accum_ = self.xyz_gradient_accum_[valid].contiguous()
-        self.denom_ = self.denom_[valid].contiguous()
-        self.max_radii2D_ = self.max_radii2D_[valid].contiguous()
-
-    def densificationPostfix(self, new_xyz, new_features_dc, new_features_rest, new_opacities, new_scaling, new_rotation):
-        """reference gaussian_model.cpp:644-714: parameters concatenated, moments zero-extended, statistics reset."""
-        ext = [new_xyz, new_features_dc, new_features_rest, new_opacities, new_scaling, new_rotation]
-        self._set([torch.cat((t, e), dim=0).contiguous() for t, e in zip(self.tensors(), ext)])
-        self.exp_avg_ = [torch.cat((t, torch.zeros_like(e)), dim=0).contiguous() for t, e in zip(self.exp_avg_, ext)]
-        self.exp_avg_sq_ = [torch.cat((t, torch.zeros_like(e)), dim=0).contiguous() for t, e in zip(self.exp_avg_sq_, ext)]
+        """reference gaussian_model.cpp:588-642 (statistics are compacted, not reset)"""
+        L = _bind()
         P = self.num_points()
-        z = lambda *sh: torch.zeros(sh, dtype=torch.float32, device=self.device)
-        self.xyz_gradient_accum_, self.denom_, self.max_radii2D_ = z(P, 1), z(P, 1), z(P)
+        stream = torch.cuda.current_stream().cuda_stream
+        ws = torch.empty(L.psb_densify_workspace_bytes(P), dtype=torch.uint8, device=self.device)
+        counts = (C.c_int * 5)()
+        m8 = mask.to(torch.uint8).contiguous()
+        _lib.check(L.psb_prune_plan(P, m8.data_ptr(), ws.data_ptr(), counts, stream), "psb_prune_plan")
+        d = self._blank(counts[0])
+        src, dst = self._src(), self._cm(d["p"], d["m"], d["v"], d["accum"], d["denom"], d["max_radii"], d["exist"])
+        _lib.check(L.psb_prune_apply(P, C.byref(src), C.byref(dst), counts[0], ws.data_ptr(), 1, stream), "psb_prune_apply")
+        self._adopt(d)
 
-    @staticmethod
-    def build_rotation(r):
-        """reference include/general_utils.h:31-56"""
-        q = r / torch.sqrt((r * r).sum(dim=1, keepdim=True))
-        w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
-        R = torch.zeros((q.size(0), 3, 3), device=r.device)
-        R[:, 0, 0] = 1 - 2 * (y * y + z * z); R[:, 0, 1] = 2 * (x * y - w * z); R[:, 0, 2] = 2 * (x * z + w * y)
-        R[:, 1, 0] = 2 * (x * y + w * z); R[:, 1, 1] = 1 - 2 * (x * x + z * z); R[:, 1, 2] = 2 * (y * z - w * x)
-        R[:, 2, 0] = 2 * (x * z - w * y); R[:, 2, 1] = 2 * (y * z + w * x); R[:, 2, 2] = 1 - 2 * (x * x + y * y)
-        return R
+    def densifyAndPrune(self, max_grad, min_opacity, extent, max_screen_size, seed=0, offset=None, samples=None):
+        """reference gaussian_model.cpp:795-815 with densifyAndClone / densifyAndSplit / prunePoints / densificationPostfix folded
+        into one plan + one scatter pass. The split draw is Philox(seed, offset) — identical on every data-parallel replica —
+        unless `samples` ([2 * n_split, 3] standard normals in the reference's repeat order) is injected (tests).
+        Returns (P_new, kept originals, clones, kept split children per copy, split-selected)."""
+        L = _bind()
+        P = self.num_points()
+        stream = torch.cuda.current_stream().cuda_stream
+        cfg = _DensifyCfg(float(max_grad), float(min_opacity), float(extent), float(self.percent_dense_), int(max_screen_size or 0), int(seed),
+                          int(self.step_ if offset is None else offset))
+        ws = torch.empty(L.psb_densify_workspace_bytes(P), dtype=torch.uint8, device=self.device)
+        counts = (C.c_int * 5)()
+        src = self._src()
+        _lib.check(L.psb_densify_plan(P, C.byref(src), C.byref(cfg), ws.data_ptr(), counts, stream), "psb_densify_plan")
+        if samples is not None:
+            samples = samples.to(self.device, torch.float32).contiguous()
+            assert samples.shape == (2 * counts[4], 3), (samples.shape, counts[4])
+        d = self._blank(counts[0])
+        dst = self._cm(d["p"], d["m"], d["v"], d["accum"], d["denom"], d["max_radii"], d["exist"])
+        _lib.check(L.psb_densify_apply(P, C.byref(src), C.byref(dst), counts[0], C.byref(cfg), ws.data_ptr(),
+                                       samples.data_ptr() if samples is not None and samples.numel() else None, stream), "psb_densify_apply")
+        self._adopt(d)
+        return tuple(counts)
 
-    def densifyAndSplit(self, grads, grad_threshold, scene_extent, N=2, generator=None):
-        """reference gaussian_model.cpp:716-761"""
-        n_init = self.num_points()
-        padded = torch.zeros(n_init, device=self.device)
-        padded[:grads.size(0)] = grads.squeeze()
-        sel = (padded >= grad_threshold) & (self.getScalingActivation().max(dim=1).values > self.percent_dense_ * scene_extent)
-        stds = self.getScalingActivation()[sel].repeat(N, 1)
-        samples = torch.normal(torch.zeros_like(stds), stds, generator=generator)
-        rots = self.build_rotation(self.rotation_[sel]).repeat(N, 1, 1)
-        new_xyz = torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1) + self.xyz_[sel].repeat(N, 1)
-        new_scaling = torch.log(self.getScalingActivation()[sel].repeat(N, 1) / (0.8 * N))
-        self.densificationPostfix(new_xyz, self.features_dc_[sel].repeat(N, 1, 1), self.features_rest_[sel].repeat(N, 1, 1),
-                                  self.opacity_[sel].repeat(N, 1), new_scaling, self.rotation_[sel].repeat(N, 1))
-        prune_filter = torch.cat((sel, torch.zeros(N * int(sel.sum().item()), dtype=torch.bool, device=self.device)))
-        self.prunePoints(prune_filter)
+    def densifySplitCount(self, max_grad, extent):
+        """number of rows densifyAndSplit would select right now (plan only; for tests that inject the normal draw)"""
+        L = _bind()
+        P = self.num_points()
+        cfg = _DensifyCfg(float(max_grad), 0.0, float(extent), float(self.percent_dense_), 0, 0, 0)
+        ws = torch.empty(L.psb_densify_workspace_bytes(P), dtype=torch.uint8, device=self.device)
+        counts = (C.c_int * 5)()
+        src = self._src()
+        _lib.check(L.psb_densify_plan(P, C.byref(src), C.byref(cfg), ws.data_ptr(), counts, torch.cuda.current_stream().cuda_stream), "psb_densify_plan")
+        return counts[4]
 
-    def densifyAndClone(self, grads, grad_threshold, scene_extent):
-        """reference gaussian_model.cpp:763-793"""
-        sel = (torch.norm(grads, dim=-1) >= grad_threshold) & (self.getScalingActivation().max(dim=1).values <= self.percent_dense_ * scene_extent)
-        self.densificationPostfix(self.xyz_[sel], self.features_dc_[sel], self.features_rest_[sel], self.opacity_[sel], self.scaling_[sel],
-                                  self.rotation_[sel])
-
-    def densifyAndPrune(self, max_grad, min_opacity, extent, max_screen_size, generator=None):
-        """reference gaussian_model.cpp:795-815"""
-        grads = self.xyz_gradient_accum_ / self.denom_
-        grads[grads.isnan()] = 0.0
-        self.densifyAndClone(grads, max_grad, extent)
-        self.densifyAndSplit(grads, max_grad, extent, generator=generator)
-        prune_mask = (self.getOpacityActivation() < min_opacity).squeeze()
-        if max_screen_size:
-            big_vs = self.max_radii2D_ > max_screen_size
-            big_ws = self.getScalingActivation().max(dim=1).values > 0.1 * extent
-            prune_mask = prune_mask | big_vs | big_ws
-        self.prunePoints(prune_mask)
-
-    def increasePcd(self, points, colors):
-        """reference gaussian_model.cpp:193-290: new Gaussians from sparse points — RGB2SH colour, scale from the
-        3-NN mean distance (distCUDA2 = psb_dist_cuda2), identity rotation, opacity = logit(0.1)."""
+    def increasePcd(self, points, colors, iteration=0):
+        """reference gaussian_model.cpp:193-377 (both overloads: host vectors / tensors): new Gaussians from sparse points — RGB2SH
+        colour, scale from the 3-NN mean distance (distCUDA2 = psb_dist_cuda2), identity rotation, opacity = logit(0.1)."""
         from .points import distCUDA2
-        if points.numel() == 0:
+        L = _bind()
+        points = torch.as_tensor(points, dtype=torch.float32).reshape(-1, 3)
+        colors = torch.as_tensor(colors, dtype=torch.float32).reshape(-1, 3)
+        n = points.size(0)
+        if n == 0:
             return
-        pts = points.to(self.device, torch.float32).contiguous()
-        M = (self.max_sh_degree_ + 1) ** 2
-        f_dc = ((colors.to(self.device, torch.float32) - 0.5) / 0.28209479177387814).unsqueeze(1).contiguous()
-        f_rest = torch.zeros((pts.size(0), M - 1, 3), device=self.device)
-        dist2 = torch.clamp_min(distCUDA2(pts.clone()), 0.0000001)
-        scales = torch.log(torch.sqrt(dist2)).unsqueeze(1).repeat(1, 3)
-        rots = torch.zeros((pts.size(0), 4), device=self.device)
-        rots[:, 0] = 1
-        opac = torch.full((pts.size(0), 1), math.log(0.1 / 0.9), device=self.device)
-        self.densificationPostfix(pts, f_dc, f_rest, opac, scales, rots)
+        pts = points.to(self.device).contiguous()
+        cols = colors.to(self.device).contiguous()
+        if getattr(self, "sparse_points_xyz_", None) is None or self.sparse_points_xyz_.numel() == 0:
+            self.sparse_points_xyz_, self.sparse_points_color_ = pts, cols
+        else:
+            self.sparse_points_xyz_ = torch.cat((self.sparse_points_xyz_, pts), dim=0)
+            self.sparse_points_color_ = torch.cat((self.sparse_points_color_, cols), dim=0)
+        dist2 = distCUDA2(pts)
+        P = self.num_points()
+        if not hasattr(self, "exp_avg_"):
+            raise RuntimeError("increasePcd: call trainingSetup() first (the optimizer state is extended together with the parameters)")
+        d = self._blank(P + n)
+        src, dst = self._src(), self._cm(d["p"], d["m"], d["v"], d["accum"], d["denom"], d["max_radii"], d["exist"])
+        _lib.check(L.psb_insert_points(P, C.byref(src), C.byref(dst), n, pts.data_ptr(), cols.data_ptr(), dist2.data_ptr(), int(iteration),
+                                       torch.cuda.current_stream().cuda_stream), "psb_insert_points")
+        self._adopt(d)
+
+    # --- loop closure / scale refinement (reference gaussian_model.cpp:379-475)
+    def scaledTransformationPostfix(self, new_xyz, new_scaling):
+        """:403-418: the two tensors replace xyz / scaling in the optimizer with FRESH (zero) moments (replaceTensorToOptimizer :567-586)"""
+        self.xyz_, self.scaling_ = new_xyz.contiguous(), new_scaling.contiguous()
+        for i in (0, 4):
+            self.exp_avg_[i] = torch.zeros_like(self.tensors()[i])
+            self.exp_avg_sq_[i] = torch.zeros_like(self.tensors()[i])
+
+    def applyScaledTransformation(self, s, T):
+        """:379-401: xyz <- T (s * xyz) through transformPoints; scaling_ (the LOG scale) is multiplied by s like the reference does.
+        T: [4,4] row-major world transform (Sophus::SE3f::matrix())."""
+        from .points import transformPoints
+        T_tensor = torch.as_tensor(T, dtype=torch.float32, device=self.device).reshape(4, 4).transpose(0, 1).contiguous()
+        xyz = transformPoints(self.xyz_ * float(s), T_tensor)
+        self.scaledTransformationPostfix(xyz, self.scaling_ * float(s))
+
+    def scaledTransformVisiblePointsOfKeyframe(self, point_not_transformed_flags, diff_pose, kf_world_view_transform, kf_full_proj_transform,
+                                               kf_creation_iter, stable_num_iter_existence, num_transformed=0, scale=1.0):
+        """:420-475: Gaussians younger than `stable_num_iter_existence` relative to the keyframe, not yet transformed and in front of it
+        are moved by diff_pose (operate_points.cu:95-143); xyz and rotation (ACTIVATED, as in the reference) re-enter the optimizer with
+        zero moments. Returns the updated num_transformed."""
+        from .points import scaleAndTransformThenMarkVisiblePoints
+        points = self.xyz_.clone()
+        rots = self.getRotationActivation()
+        unstable = (self._exist() - int(kf_creation_iter)).abs() < int(stable_num_iter_existence)
+        num_transformed = scaleAndTransformThenMarkVisiblePoints(points, rots, point_not_transformed_flags, unstable, diff_pose,
+                                                                 kf_world_view_transform, kf_full_proj_transform, num_transformed, scale)
+        self.xyz_, self.rotation_ = points.contiguous(), rots.contiguous()
+        for i in (0, 5):
+            self.exp_avg_[i] = torch.zeros_like(self.tensors()[i])
+            self.exp_avg_sq_[i] = torch.zeros_like(self.tensors()[i])
+        return num_transformed
 
     def _cmodel(self, with_state=True):
         m = _Model()
@@ -440,7 +510,8 @@ class GaussianTrainer:
         """Waits until every enqueued iteration has finished on the device."""
         torch.cuda.current_stream().synchronize()
 
-    STAGES = ("preprocess", "depth_sort_scan", "binning", "render_fwd", "loss", "render_bwd", "backward_adam")
+    STAGES = ("preprocess", "depth_sort_scan", "binning", "render_fwd", "loss", "render_bwd", "gaussian_backward", "frest_adam")
+    DP_STAGES = ("preprocess", "depth_sort_scan", "binning", "render_fwd", "loss", "render_bwd", "push_backward", "wait_grads", "shard_adam", "wait_params")
 
     def set_profiling(self, enable=True):
         self.L.psb_trainer_set_profiling.argtypes = [C.c_void_p, C.c_int]
@@ -448,10 +519,11 @@ class GaussianTrainer:
 
     def stage_times(self):
         """ms per stage of the last profiled step (CUDA events on the step's stream)."""
-        ms = (C.c_float * 7)()
+        ms = (C.c_float * 10)()
         self.L.psb_trainer_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
-        _lib.check(self.L.psb_trainer_stage_times(self.h, ms, 7), "psb_trainer_stage_times")
-        return dict(zip(self.STAGES, [float(x) for x in ms]))
+        n = _lib.check(self.L.psb_trainer_stage_times(self.h, ms, 10), "psb_trainer_stage_times")
+        names = self.DP_STAGES if n == 10 else self.STAGES
+        return dict(zip(names[:n], [float(x) for x in ms][:n]))
 
     def trainingOnce(self, cam, gt_image, mask=None):
         """Reference-style blocking iteration: returns the loss like loss.item() (gaussian_mapper.cpp:705)."""

@@ -70,3 +70,23 @@ def test_model_snapshot_restore_and_ply_roundtrip_on_cpu(tmp_path):
     assert m2.active_sh_degree_ == 3
     for a, b in zip(m.tensors(), m2.tensors()):
         assert a.shape == b.shape and torch.equal(a, b)
+
+
+def test_libtorch_cpu_sh_baseline_matches_the_host_sh_utils():
+    """oracle/ref_sh_loss_cpu.py (reference include/sh_utils.h:64-136 as ATen CPU ops — the reported LibTorch-CPU baseline of bench.py)
+    and photo_slam_b200/sh_utils.py (numpy) evaluate the same polynomial."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import numpy as np
+    import torch
+    import ref_sh_loss_cpu
+    import photo_slam_b200.sh_utils as su
+    rng = np.random.default_rng(0)
+    sh = rng.normal(size=(200, 3, 16)).astype(np.float32)
+    d = rng.normal(size=(200, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    for deg in range(4):
+        a = ref_sh_loss_cpu.eval_sh(deg, torch.from_numpy(sh), torch.from_numpy(d)).numpy()
+        b = su.eval_sh(deg, sh, d)
+        assert np.allclose(a, b, rtol=1e-5, atol=1e-6), deg

@@ -119,3 +119,54 @@ def test_knn_matches_bruteforce_numpy():
     np.fill_diagonal(d, np.inf)
     ref = np.sort(d, axis=1)[:, :3].mean(1)
     assert np.allclose(oracle_c.knn_mean_dist2(pts), ref, rtol=1e-5)
+
+
+def _densify_state(P, seed, extent):
+    """A model with every densification case present: never-seen rows (0/0), clone and split candidates, transparent and oversized rows."""
+    import photo_slam_b200.synthetic as syn
+    rng = np.random.default_rng(seed)
+    sc = syn.make_scene(P, syn.make_camera(160, 120, 130.0, 130.0), seed=seed)
+    p = [sc["xyz"], sc["features_dc"], sc["features_rest"], sc["opacity"], sc["scaling"].copy(), sc["rotation"]]
+    p[4][rng.choice(P, P // 50, replace=False)] = np.log(0.2 * extent)        # > 0.1 extent: world-size prune
+    m = [rng.uniform(-1, 1, a.shape).astype(np.float32) for a in p]
+    v = [rng.uniform(0, 1, a.shape).astype(np.float32) for a in p]
+    accum = (rng.uniform(0, 0.004, (P, 1))).astype(np.float32)
+    denom = np.full((P, 1), 2.0, np.float32)
+    denom[::10] = 0.0
+    accum[::10] = 0.0                                                          # 0/0 -> nan -> 0
+    maxr = rng.uniform(0, 50, P).astype(np.float32)
+    return p, m, v, accum, denom, maxr
+
+
+@pytest.mark.parametrize("max_screen_size", [0, 20])
+def test_densify_oracle_matches_aten_restatement(max_screen_size):
+    """oracle/gs_oracle.c:orc_densify_and_prune (step-by-step C restatement of gaussian_model.cpp:588-815) pinned to the ATen ops the
+    reference calls (oracle/ref_densify.py on CPU tensors): identical selection, compaction order and counts; values to 1e-6."""
+    import torch
+    import ref_densify
+    P, extent, pd, tau, min_op = 3000, 5.0, 0.01, 0.001, 0.3
+    p, m, v, accum, denom, maxr = _densify_state(P, 4, extent)
+    T = lambda a: torch.from_numpy(a.copy())
+    st = dict(p=[T(a) for a in p], m=[T(a) for a in m], v=[T(a) for a in v], accum=T(accum), denom=T(denom), max_radii=T(maxr))
+    ns = ref_densify.split_count(dict(st, accum=T(accum), denom=T(denom)), tau, extent, pd)
+    assert ns == oracle_c.densify_split_count(p[4], accum, denom, tau, extent, pd) and ns > 20
+    z = np.random.default_rng(1).normal(size=(2 * ns, 3)).astype(np.float32)
+    ref_densify.densify_and_prune(st, tau, min_op, extent, max_screen_size, pd, torch.from_numpy(z))
+    op, om, ov = oracle_c.densify_and_prune(p, m, v, accum, denom, maxr, tau, min_op, extent, max_screen_size, pd, z)
+    n = st["p"][0].shape[0]
+    assert op[0].shape[0] == n and n != P
+    for a, b in zip(op + om + ov, st["p"] + st["m"] + st["v"]):
+        b = b.numpy()
+        assert a.shape == b.shape
+        assert np.allclose(a, b, rtol=1e-6, atol=1e-6), np.abs(a - b).max()
+    # untouched survivors and clones are bit-exact copies; new rows have zero moments
+    assert np.array_equal(op[2], st["p"][2].numpy()) and np.array_equal(om[2], st["m"][2].numpy())
+    assert not st["accum"].any() and not st["max_radii"].any()
+
+
+def test_reset_opacity_oracle_matches_aten():
+    import torch
+    import ref_densify
+    o = np.random.default_rng(0).normal(0, 2, (500, 1)).astype(np.float32)
+    st = ref_densify.reset_opacity(dict(p=[None, None, None, torch.from_numpy(o.copy())], m=[None] * 6, v=[None] * 6))
+    assert np.allclose(oracle_c.reset_opacity(o), st["p"][3].numpy(), rtol=1e-6, atol=1e-6)

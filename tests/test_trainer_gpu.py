@@ -191,67 +191,6 @@ def test_arena_overflow_is_a_noop_then_retried(cuda):
         assert ((x - y).abs() > 0.5 * lrate).float().mean().item() < 2e-3
 
 
-def test_densify_prune_insert_mirror(cuda):
-    """Tensor surgery of reference gaussian_model.cpp:556-815 on this model's tensors + Adam moments."""
-    from photo_slam_b200 import trainer
-    P = 5000
-    sc = syn.make_scene(P, syn.make_camera(160, 120, 130.0, 130.0), seed=4)
-    m = trainer.GaussianModel.from_numpy(sc, cuda)
-    m.trainingSetup(trainer.GaussianOptimizationParams())
-    gen = torch.Generator(device=cuda).manual_seed(0)
-    for t in m.exp_avg_ + m.exp_avg_sq_:
-        t.copy_(torch.rand(t.shape, device=cuda, generator=gen))
-    m.xyz_gradient_accum_.copy_(torch.rand((P, 1), device=cuda, generator=gen) * 0.004)
-    m.denom_.fill_(2.0)
-    m.denom_[::10] = 0.0                                  # never-seen Gaussians: 0/0 -> nan -> 0
-    before = [t.clone() for t in m.tensors()]
-    mom = [t.clone() for t in m.exp_avg_]
-    extent = 5.0
-    grads = (m.xyz_gradient_accum_ / m.denom_).nan_to_num(0.0)
-    small = torch.exp(before[4]).max(dim=1).values <= 0.01 * extent
-    clone_sel = (grads.squeeze() >= 0.001) & small
-    split_sel_orig = (grads.squeeze() >= 0.001) & ~small
-    n_clone, n_split = int(clone_sel.sum()), int(split_sel_orig.sum())
-    assert n_clone > 0 and n_split > 0
-    m.densifyAndClone(grads, 0.001, extent)
-    assert m.num_points() == P + n_clone
-    assert torch.equal(m.xyz_[P:], before[0][clone_sel]) and torch.equal(m.exp_avg_[2][:P], mom[2]) and not m.exp_avg_[2][P:].any()
-    assert not m.denom_.any() and m.denom_.shape == (P + n_clone, 1)
-    m.densifyAndSplit(grads, 0.001, extent, generator=gen)
-    assert m.num_points() == P + n_clone - n_split + 2 * n_split
-    # the split children: log-scale = log(exp(s) / 1.6) of the parent, positions within a few sigma of it
-    kids = m.scaling_[-2 * n_split:]
-    parents = before[4][split_sel_orig].repeat(2, 1)
-    assert torch.allclose(kids, torch.log(torch.exp(parents) / 1.6), atol=1e-5)
-    d = (m.xyz_[-2 * n_split:] - before[0][split_sel_orig].repeat(2, 1)).norm(dim=1) / torch.exp(parents).max(dim=1).values
-    assert d.max().item() < 8.0 and d.mean().item() > 0.3
-    n0 = m.num_points()
-    prune = torch.sigmoid(m.opacity_).squeeze() < 0.05
-    m.densifyAndPrune(1e9, 0.05, extent, 0)               # thresholds chosen so only the opacity prune acts
-    assert m.num_points() == n0 - int(prune.sum())
-    assert all(t.size(0) == m.num_points() and t.is_contiguous() for t in m.tensors() + m.exp_avg_ + m.exp_avg_sq_)
-    # insertion: scale from the 3-NN distance, opacity logit(0.1), identity rotation, moments zero
-    pts = torch.rand((300, 3), device=cuda)
-    n1 = m.num_points()
-    m.increasePcd(pts, torch.rand((300, 3), device=cuda))
-    from photo_slam_b200.points import distCUDA2
-    assert m.num_points() == n1 + 300
-    assert torch.allclose(m.scaling_[n1:, 0], torch.log(torch.sqrt(distCUDA2(pts).clamp_min(1e-7))))
-    assert torch.allclose(torch.sigmoid(m.opacity_[n1:]), torch.full((300, 1), 0.1, device=cuda), atol=1e-6)
-    # the reference's resetOpacity keeps the opacities (quirk 9) and zeroes their moments
-    op = m.opacity_.clone()
-    m.resetOpacity()
-    assert torch.allclose(m.opacity_, op, atol=1e-4) and not m.exp_avg_[3].any()
-    # and the model still trains after the surgery
-    W, H, fx, fy = 160, 120, 130.0, 130.0
-    camn = syn.make_camera(W, H, fx, fy)
-    c = dict(viewmatrix=torch.from_numpy(camn["viewmatrix"]).to(cuda), projmatrix=torch.from_numpy(camn["projmatrix"]).to(cuda),
-             campos=torch.from_numpy(camn["campos"]).to(cuda), tanfovx=float(camn["tanfovx"]), tanfovy=float(camn["tanfovy"]), W=W, H=H)
-    tr = trainer.GaussianTrainer(m)
-    tr.trainForOneIteration(c, torch.rand((3, H, W), device=cuda))
-    assert math.isfinite(tr.result()[0])
-
-
 def test_host_front_end_matches_device_path(cuda):
     """GaussianTrainer.trainHost (pinned host inputs, copy overlapped, loss read through the early read-back event) == the plain path."""
     from photo_slam_b200 import trainer
