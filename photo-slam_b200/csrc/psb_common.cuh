@@ -196,39 +196,44 @@ struct TileCull {
 		return !(qmin > thr + pad);
 	}
 	// Bit k (row-major) = tile k of the tile rectangle [x0,x1) x [y0,y1) (at most 32 tiles) of a W x H image can be reached.
-	// Same test as reaches() per tile, with the row-only terms hoisted and ONE rounding pad for the whole rectangle
-	// (evaluated at the largest |dx|, |dy| of the rectangle, hence >= every per-tile pad: keeps a superset).
+	// O(rows), not O(tiles): the level set {q <= t} is an ellipse; over a band of tile rows dy in [lo, hi] its dx-extent is the
+	// interval [xl, xr] with the closed form  dx = (-B dy +- sqrt(2 t A - det dy^2)) / A  evaluated where the band is widest (the
+	// ellipse's own dx-extremes sit at dy = -+B sqrt(2t / (det C)), clamped into the band). A tile of the row is kept iff its
+	// pixel columns meet the interval: a contiguous run of tiles -> a run of mask bits, no per-tile loop. One rounding pad (t) for the
+	// whole rectangle plus a relative pad on the interval: always a superset of the tiles with a pixel at alpha >= 1/255
+	// (numpy restatement checked against brute-force per-pixel evaluation: tests/test_cull_cpu.py).
 	__device__ __forceinline__ uint32_t rect_mask(int x0, int y0, int x1, int y1, int W, int H) const
 	{
-		const int area = (x1 - x0) * (y1 - y0);
+		const int w = x1 - x0, area = w * (y1 - y0);
 		const uint32_t full = area >= 32 ? 0xffffffffu : ((1u << area) - 1u);
 		if (none) return 0u;
-		if (all) return full;
+		const float det = __fsub_rn(__fmul_rn(A, C), __fmul_rn(B, B));
+		if (all || !(det > 0.f)) return full;
 		const float DX = fmaxf(fabsf(mx - (float)(x0 * PSB_TILE_X)), fabsf(mx - (float)(min(x1 * PSB_TILE_X, W) - 1)));
 		const float DY = fmaxf(fabsf(my - (float)(y0 * PSB_TILE_Y)), fabsf(my - (float)(min(y1 * PSB_TILE_Y, H) - 1)));
-		const float thrp = thr + __fmaf_rn(1e-5f, splat_q(A, fabsf(B), C, DX, DY), 1e-4f);
-		uint32_t mask = 0u, bit = 1u;
+		const float t = thr + __fmaf_rn(1e-5f, splat_q(A, fabsf(B), C, DX, DY), 1e-4f);
+		const float t2 = 2.f * t;
+		const float Y = sqrtf(__fdiv_rn(__fmul_rn(t2, A), det));                       // |dy| extent of the ellipse
+		const float dyr = __fmul_rn(-B, sqrtf(__fdiv_rn(t2, __fmul_rn(det, C))));      // dy at which dx is largest
+		const float invA = __fdiv_rn(1.f, A), t2A = __fmul_rn(t2, A);
+		uint32_t mask = 0u;
 		for (int ty = y0; ty < y1; ty++) {
 			const int py0 = ty * PSB_TILE_Y;
 			const float dylo = my - (float)(min(py0 + PSB_TILE_Y, H) - 1), dyhi = my - (float)py0;
-			const bool yin = dylo <= 0.f && dyhi >= 0.f;
-			const float ey = dylo > 0.f ? dylo : dyhi;  // horizontal edge facing the centre (when !yin)
-			const float sxu = nba * ey, by = B * ey, cy = 0.5f * C * ey * ey;
-			for (int tx = x0; tx < x1; tx++, bit <<= 1) {
-				const int px0 = tx * PSB_TILE_X;
-				const float dxlo = mx - (float)(min(px0 + PSB_TILE_X, W) - 1), dxhi = mx - (float)px0;
-				const bool xin = dxlo <= 0.f && dxhi >= 0.f;
-				float qmin = (xin && yin) ? 0.f : 3.0e38f;
-				if (!xin) {
-					const float ex = dxlo > 0.f ? dxlo : dxhi;
-					qmin = splat_q(A, B, C, ex, fminf(fmaxf(nbc * ex, dylo), dyhi));
-				}
-				if (!yin) {
-					const float s2 = fminf(fmaxf(sxu, dxlo), dxhi);
-					qmin = fminf(qmin, __fmaf_rn(__fmaf_rn(0.5f * A, s2, by), s2, cy));
-				}
-				if (!(qmin > thrp)) mask |= bit;
-			}
+			const float lo = fmaxf(dylo, -Y), hi = fminf(dyhi, Y);
+			if (lo > hi) continue;                                                       // the band misses the ellipse
+			const float ya = fminf(fmaxf(dyr, lo), hi), yb = fminf(fmaxf(-dyr, lo), hi);
+			const float Da = fmaxf(__fsub_rn(t2A, __fmul_rn(__fmul_rn(det, ya), ya)), 0.f);
+			const float Db = fmaxf(__fsub_rn(t2A, __fmul_rn(__fmul_rn(det, yb), yb)), 0.f);
+			float xr = __fmul_rn(__fadd_rn(__fmul_rn(-B, ya), sqrtf(Da)), invA);
+			float xl = __fmul_rn(__fsub_rn(__fmul_rn(-B, yb), sqrtf(Db)), invA);
+			const float e = __fmul_rn(1e-4f, __fadd_rn(fmaxf(fabsf(xl), fabsf(xr)), 1.f));
+			xr = __fadd_rn(xr, e); xl = __fsub_rn(xl, e);
+			// tile tx holds pixel columns [16 tx, 16 tx + 15] (the image edge only shortens it: treating it as full keeps a superset);
+			// dx = mx - column: kept iff  mx - xr <= 16 tx + 15  and  16 tx <= mx - xl
+			const int tlo = max(x0, (int)ceilf(__fmul_rn(__fsub_rn(__fsub_rn(mx, xr), 15.f), 0.0625f)));
+			const int thi = min(x1 - 1, (int)floorf(__fmul_rn(__fsub_rn(mx, xl), 0.0625f)));
+			if (tlo <= thi) mask |= ((2u << (thi - tlo)) - 1u) << ((ty - y0) * w + (tlo - x0));
 		}
 		return mask;
 	}

@@ -15,7 +15,6 @@ namespace psb {
 
 namespace {
 
-constexpr int KNN_BOX = 1024;
 
 __device__ __forceinline__ uint32_t f2ord(float f) { const uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
 __device__ __forceinline__ float ord2f(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o); }
@@ -63,81 +62,119 @@ __global__ void knn_morton_kernel(int P, const float* __restrict__ pts, const ui
 	codes[i] = code;
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Exact 3-nearest-neighbour search, block-cooperative (the reference, simple_knn.cu:147-183, lets every thread walk all boxes
+// of 1024 points on its own, gathering candidates one by one from global memory through the Morton permutation).
+//
+//   * the points are copied once into Morton order as float4 (xyz + original index): candidate tiles are contiguous;
+//   * a block owns one tile of 256 queries (one per thread, in registers) and visits the candidate tiles outwards from its own
+//     (b, b+1, b-1, b+2, ...: Morton neighbours first, so the 3rd-best distances shrink early);
+//   * a tile is skipped for the WHOLE block when the gap between the two tiles' bounding boxes exceeds the largest 3rd-best
+//     distance any query of the block still has (one uniform test per tile pair instead of 256 per-thread box tests);
+//   * a tile that survives is staged in shared memory once (coalesced 16-byte loads) and every query that its own point-to-box
+//     test lets through scans it there: all lanes read the same candidate -> shared-memory broadcasts instead of gathers;
+//   * the three smallest squared distances are kept by a branch-free min/max insertion network.
+// The result is the exact 3-NN mean of squared distances like the reference's (any exact search returns the same three values).
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int KNN_TILE = 256;
 struct Box { float mn[3], mx[3]; };
 
-__global__ void __launch_bounds__(KNN_BOX) knn_box_kernel(int P, const float* __restrict__ pts, const uint32_t* __restrict__ order, Box* __restrict__ boxes)
+__global__ void knn_gather_kernel(int P, const float* __restrict__ pts, const uint32_t* __restrict__ order, float4* __restrict__ sorted)
 {
-	__shared__ float s_mn[3][32], s_mx[3][32];
-	const int i = blockIdx.x * KNN_BOX + threadIdx.x;
-	float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P) return;
+	const uint32_t g = order[i];
+	sorted[i] = make_float4(pts[3 * g], pts[3 * g + 1], pts[3 * g + 2], __uint_as_float(g));
+}
+
+__global__ void __launch_bounds__(KNN_TILE) knn_tile_box_kernel(int P, const float4* __restrict__ sorted, Box* __restrict__ boxes)
+{
+	__shared__ float s_red[6][KNN_TILE / 32];
+	const int i = blockIdx.x * KNN_TILE + threadIdx.x;
+	float v[6] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
 	if (i < P) {
-		const uint32_t g = order[i];
-#pragma unroll
-		for (int c = 0; c < 3; c++) mn[c] = mx[c] = pts[3 * g + c];
+		const float4 p = sorted[i];
+		v[0] = v[3] = p.x; v[1] = v[4] = p.y; v[2] = v[5] = p.z;
 	}
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-	for (int c = 0; c < 3; c++) {
+	for (int c = 0; c < 6; c++) {
 #pragma unroll
-		for (int o = 16; o > 0; o >>= 1) { mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o)); mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o)); }
-		if (lane == 0) { s_mn[c][warp] = mn[c]; s_mx[c][warp] = mx[c]; }
+		for (int o = 16; o > 0; o >>= 1) {
+			const float u = __shfl_xor_sync(0xffffffffu, v[c], o);
+			v[c] = c < 3 ? fminf(v[c], u) : fmaxf(v[c], u);
+		}
+		if (lane == 0) s_red[c][warp] = v[c];
 	}
 	__syncthreads();
-	if (warp == 0) {
+	if (threadIdx.x < 6) {
+		const int c = threadIdx.x;
+		float r = s_red[c][0];
 #pragma unroll
-		for (int c = 0; c < 3; c++) {
-			float a = s_mn[c][lane], b = s_mx[c][lane];
-#pragma unroll
-			for (int o = 16; o > 0; o >>= 1) { a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o)); b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o)); }
-			if (lane == 0) { boxes[blockIdx.x].mn[c] = a; boxes[blockIdx.x].mx[c] = b; }
-		}
+		for (int w = 1; w < KNN_TILE / 32; w++) r = c < 3 ? fminf(r, s_red[c][w]) : fmaxf(r, s_red[c][w]);
+		if (c < 3) boxes[blockIdx.x].mn[c] = r;
+		else boxes[blockIdx.x].mx[c - 3] = r;
 	}
 }
 
-__device__ __forceinline__ void kbest3(const float3 ref, const float3 p, float* best)
-{
-	const float3 d = make_float3(p.x - ref.x, p.y - ref.y, p.z - ref.z);
-	float dist = d.x * d.x + d.y * d.y + d.z * d.z;
-#pragma unroll
-	for (int j = 0; j < 3; j++) {
-		if (best[j] > dist) { const float t = best[j]; best[j] = dist; dist = t; }
-	}
-}
-__device__ __forceinline__ float box_dist(const Box& b, const float3 p)
-{
-	float3 diff = make_float3(0, 0, 0);
-	if (p.x < b.mn[0] || p.x > b.mx[0]) diff.x = fminf(fabsf(p.x - b.mn[0]), fabsf(p.x - b.mx[0]));
-	if (p.y < b.mn[1] || p.y > b.mx[1]) diff.y = fminf(fabsf(p.y - b.mn[1]), fabsf(p.y - b.mx[1]));
-	if (p.z < b.mn[2] || p.z > b.mx[2]) diff.z = fminf(fabsf(p.z - b.mn[2]), fabsf(p.z - b.mx[2]));
-	return diff.x * diff.x + diff.y * diff.y + diff.z * diff.z;
-}
+__device__ __forceinline__ float axis_gap(float lo_a, float hi_a, float lo_b, float hi_b) { return fmaxf(0.f, fmaxf(lo_b - hi_a, lo_a - hi_b)); }
 
-// exact 3-NN with box pruning (same search as reference simple_knn.cu:147-183)
-__global__ void knn_mean_dist_kernel(int P, const float* __restrict__ pts, const uint32_t* __restrict__ order, const Box* __restrict__ boxes,
-                                     float* __restrict__ dists)
+__global__ void __launch_bounds__(KNN_TILE) knn_search_kernel(int P, int ntile, const float4* __restrict__ sorted, const Box* __restrict__ boxes,
+                                                            float* __restrict__ dists)
 {
-	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= P) return;
-	auto pt = [&](int k) { const uint32_t g = order[k]; return make_float3(pts[3 * g], pts[3 * g + 1], pts[3 * g + 2]); };
-	const float3 point = pt(idx);
-	float best[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
-	for (int i = max(0, idx - 3); i <= min(P - 1, idx + 3); i++) {
-		if (i == idx) continue;
-		kbest3(point, pt(i), best);
-	}
-	const float reject = best[2];
-	best[0] = best[1] = best[2] = FLT_MAX;
-	const int nbox = (P + KNN_BOX - 1) / KNN_BOX;
-	for (int b = 0; b < nbox; b++) {
-		const float dist = box_dist(boxes[b], point);
-		if (dist > reject || dist > best[2]) continue;
-		const int e = min(P, (b + 1) * KNN_BOX);
-		for (int i = b * KNN_BOX; i < e; i++) {
-			if (i == idx) continue;
-			kbest3(point, pt(i), best);
+	__shared__ float4 s_tile[KNN_TILE];
+	__shared__ float s_wmax[KNN_TILE / 32];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int my = blockIdx.x;
+	const int qi = my * KNN_TILE + tid;
+	const bool valid = qi < P;
+	const float4 q = valid ? sorted[qi] : make_float4(0.f, 0.f, 0.f, 0.f);
+	const Box Q = boxes[my];
+	float b0 = FLT_MAX, b1 = FLT_MAX, b2 = FLT_MAX;   // three smallest squared distances, ascending
+	float rmax = FLT_MAX;                              // largest b2 over the block's queries (uniform)
+	const int reach = max(my, ntile - 1 - my);
+	for (int k = 0; k <= reach; k++) {
+#pragma unroll
+		for (int side = 0; side < 2; side++) {
+			const int t = side == 0 ? my + k : my - k;
+			if ((side == 1 && k == 0) || t < 0 || t >= ntile) continue;   // uniform
+			const Box B = boxes[t];
+			const float gx = axis_gap(Q.mn[0], Q.mx[0], B.mn[0], B.mx[0]), gy = axis_gap(Q.mn[1], Q.mx[1], B.mn[1], B.mx[1]),
+			            gz = axis_gap(Q.mn[2], Q.mx[2], B.mn[2], B.mx[2]);
+			if (gx * gx + gy * gy + gz * gz > rmax) continue;             // no query of this block can gain from that tile (uniform)
+			__syncthreads();                                               // previous tile fully consumed
+			const int ci = t * KNN_TILE + tid;
+			s_tile[tid] = ci < P ? sorted[ci] : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0.f);
+			__syncthreads();
+			if (valid) {
+				const float px = axis_gap(q.x, q.x, B.mn[0], B.mx[0]), py = axis_gap(q.y, q.y, B.mn[1], B.mx[1]), pz = axis_gap(q.z, q.z, B.mn[2], B.mx[2]);
+				if (!(px * px + py * py + pz * pz > b2)) {
+					const int self = t == my ? tid : -1;
+					const int cnt = min(KNN_TILE, P - t * KNN_TILE);
+					for (int j = 0; j < cnt; j++) {
+						const float4 c = s_tile[j];
+						const float dx = c.x - q.x, dy = c.y - q.y, dz = c.z - q.z;
+						float d = dx * dx + dy * dy + dz * dz;
+						if (j == self) d = FLT_MAX;
+						const float t0 = fmaxf(b0, d); b0 = fminf(b0, d);
+						const float t1 = fmaxf(b1, t0); b1 = fminf(b1, t0);
+						b2 = fminf(b2, t1);
+					}
+				}
+			}
+			// refresh the block-wide bound
+			float m = valid ? b2 : 0.f;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+			__syncthreads();
+			if (lane == 0) s_wmax[warp] = m;
+			__syncthreads();
+			rmax = s_wmax[0];
+#pragma unroll
+			for (int w = 1; w < KNN_TILE / 32; w++) rmax = fmaxf(rmax, s_wmax[w]);
 		}
 	}
-	dists[order[idx]] = (best[0] + best[1] + best[2]) / 3.0f;
+	if (valid) dists[__float_as_uint(q.w)] = (b0 + b1 + b2) / 3.0f;
 }
 
 __global__ void transform_points_kernel(int P, const float* __restrict__ pts, const float* __restrict__ m, float* __restrict__ out)
@@ -277,8 +314,8 @@ int psb_dist_cuda2(int P, const float* points, float* mean_dists, void* stream_)
 	if (P == 0) return 0;
 	const SortPlan plan = make_sort_plan(30);
 	const size_t sb = sort_scratch_bytes((size_t)P, plan.npass);
-	const int nbox = (P + KNN_BOX - 1) / KNN_BOX;
-	const size_t bytes = align_up((size_t)P * 4, 256) * 4 + align_up(sb, 256) + align_up((size_t)nbox * sizeof(Box), 256) + 256;
+	const int nbox = (P + KNN_TILE - 1) / KNN_TILE;
+	const size_t bytes = align_up((size_t)P * 4, 256) * 4 + align_up(sb, 256) + align_up((size_t)nbox * sizeof(Box), 256) + align_up((size_t)P * sizeof(float4), 256) + 512;
 	char* mem = nullptr;
 	PSB_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&mem), bytes, stream));
 	char* c = mem;
@@ -287,6 +324,7 @@ int psb_dist_cuda2(int P, const float* points, float* mean_dists, void* stream_)
 	vals[0] = carve<uint32_t>(c, P, 256); vals[1] = carve<uint32_t>(c, P, 256);
 	char* scratch = carve<char>(c, sb, 256);
 	Box* boxes = carve<Box>(c, nbox, 256);
+	float4* sorted = carve<float4>(c, P, 256);
 	uint32_t* bounds = carve<uint32_t>(c, 8, 32);
 	init_bounds_kernel<<<1, 32, 0, stream>>>(bounds);
 	int grid = cdiv(P, 256);
@@ -297,8 +335,9 @@ int psb_dist_cuda2(int P, const float* points, float* mean_dists, void* stream_)
 	int rc = radix_sort_pairs(keys, vals, /*iota_vals=*/true, nullptr, (size_t)P, plan, scratch, sb, stream);
 	if (rc == 0) {
 		const uint32_t* order = vals[plan.npass & 1];
-		knn_box_kernel<<<nbox, KNN_BOX, 0, stream>>>(P, points, order, boxes);
-		knn_mean_dist_kernel<<<cdiv(P, 128), 128, 0, stream>>>(P, points, order, boxes, mean_dists);
+		knn_gather_kernel<<<cdiv(P, 256), 256, 0, stream>>>(P, points, order, sorted);
+		knn_tile_box_kernel<<<nbox, KNN_TILE, 0, stream>>>(P, sorted, boxes);
+		knn_search_kernel<<<nbox, KNN_TILE, 0, stream>>>(P, nbox, sorted, boxes, mean_dists);
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess) { set_error("knn kernels", e, __FILE__, __LINE__); rc = PSB_ERR_CUDA; }
 	}

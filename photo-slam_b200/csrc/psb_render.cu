@@ -256,10 +256,10 @@ __device__ __forceinline__ float warp_reduce9(const float v[9], int lane)
 template <int PPT>
 struct BwdSmem {
 	static constexpr int RBB = TileGeom<PPT>::THREADS < 128 ? TileGeom<PPT>::THREADS : 128;
-	static constexpr int ACC_ROW = TileGeom<PPT>::NWARPS * 9 + 1;  // floats per entry: NWARPS x 9 sums (+1 pad: conflict-free row reads)
+	// floats per entry: NWARPS x (9 sums + 1 marker: != 0 when that warp wrote its sums for this entry), +1 pad (odd stride: conflict-free row reads)
+	static constexpr int ACC_ROW = TileGeom<PPT>::NWARPS * 10 + 1;
 	GaussRec rec[2][RBB];
 	float acc[RBB * ACC_ROW];
-	unsigned long long dirty[RBB];  // byte w != 0: warp w wrote its 9 sums for this entry
 	uint32_t gid[2][RBB];
 	uint64_t bar[2];
 	int wcnt[TileGeom<PPT>::NWARPS];
@@ -292,7 +292,10 @@ __global__ void __launch_bounds__(TileGeom<PPT>::THREADS, PPT == 2 ? PSB_BWD_MIN
 
 	const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
 
-	float pixfy[PPT], T_final[PPT], T[PPT], accum_rec[PPT][3], dL_dpixel[PPT][3], last_alpha[PPT], last_color[PPT][3], bg_dot_dpixel[PPT];
+	// Per-pixel state of the back-to-front sweep. The reference keeps accum_rec[3] and last_color[3] per pixel and evaluates
+	// dL/dalpha = sum_ch (c_ch - accum_rec_ch) dL/dpix_ch (backward.cu:497-510). dL/dpix is constant along the sweep and the accum_rec
+	// recursion is linear, so its DOT with dL/dpix obeys the same recursion: two scalars (acc_dot, last_cdot) replace six.
+	float pixfy[PPT], T_final[PPT], T[PPT], acc_dot[PPT], last_cdot[PPT], dL_dpixel[PPT][3], last_alpha[PPT], bg_dot_dpixel[PPT];
 	int last_contributor[PPT];
 	int my_max = 0;
 #pragma unroll
@@ -307,10 +310,10 @@ __global__ void __launch_bounds__(TileGeom<PPT>::THREADS, PPT == 2 ? PSB_BWD_MIN
 		my_max = max(my_max, last_contributor[p]);
 		last_alpha[p] = 0;
 		bg_dot_dpixel[p] = 0;
+		acc_dot[p] = 0.f;
+		last_cdot[p] = 0.f;
 #pragma unroll
 		for (int i = 0; i < 3; i++) {
-			accum_rec[p][i] = 0.f;
-			last_color[p][i] = 0.f;
 			dL_dpixel[p][i] = inside ? dL_dpixels[i * HW + pix_id] : 0.f;
 			bg_dot_dpixel[p] += bg_color[i] * dL_dpixel[p][i];
 		}
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(TileGeom<PPT>::THREADS, PPT == 2 ? PSB_BWD_MIN
 	const int warp_maxc = __reduce_max_sync(0xffffffffu, my_max);
 	if (lane == 0) sm.wcnt[warp] = warp_maxc;
 	if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); mbar_fence_init(); }
-	if (tid < RBB) sm.dirty[tid] = 0ull;
+	for (int i = tid; i < RBB * G::NWARPS; i += NT) sm.acc[(i / G::NWARPS) * ACC_ROW + (i % G::NWARPS) * 10 + 9] = 0.f;  // markers
 	__syncthreads();
 	int maxc = 0;
 #pragma unroll
@@ -345,8 +348,8 @@ __global__ void __launch_bounds__(TileGeom<PPT>::THREADS, PPT == 2 ? PSB_BWD_MIN
 
 	const float ddelx_dx = 0.5 * W;
 	const float ddely_dy = 0.5 * H;
-	const int my_slot = ((lane & 1) == 0) ? warp_reduce9_index(lane) : -1;
-	unsigned char* dirty8 = reinterpret_cast<unsigned char*>(sm.dirty);
+	// after warp_reduce9 the even lanes hold the nine totals; lane 1 (idle) writes the marker in the SAME store instruction
+	const int my_slot = ((lane & 1) == 0) ? warp_reduce9_index(lane) : (lane == 1 ? 9 : -1);
 
 	for (int b = 0; b < nbatch; b++) {
 		const int st = b & 1;
@@ -398,65 +401,69 @@ __global__ void __launch_bounds__(TileGeom<PPT>::THREADS, PPT == 2 ? PSB_BWD_MIN
 				}
 				if (!__any_sync(0xffffffffu, any)) continue;
 
-				float v[9];
-#pragma unroll
-				for (int i = 0; i < 9; i++) v[i] = 0.f;
+				// Per pixel only the weight w = G dL/dG is formed; the warp reduces the six MOMENTS of w over the pixel offsets
+				// (sum w, w dx, w dy, w dx^2, w dx dy, w dy^2) plus the three colour sums, and the flush turns the moments into the
+				// reference's nine sums once per (Gaussian, tile) (backward.cu:518-547):
+				//   dL/dmean2D = -(A Mx + B My) ddelx_dx, -(C My + B Mx) ddely_dy;  dL/dconic = -0.5 (Mxx, Mxy, Myy);  dL/dopacity = M0 / opacity
+				// (dG/ddel = -G (A dx + B dy): linear in the offsets). A thread's pixels share the column, so dx multiplies their sums once.
 				const float4 q2 = sm.rec[st][j].q2;
-				const float col[3] = {q2.x, q2.y, q2.z};
+				float W0 = 0.f, Wy = 0.f, Wyy = 0.f, vc0 = 0.f, vc1 = 0.f, vc2 = 0.f;
 #pragma unroll
 				for (int p = 0; p < PPT; p++) {
 					if (!active[p]) continue;
 					T[p] = T[p] / (1.f - alpha[p]);
-					const float dchannel_dcolor = alpha[p] * T[p];
-					float dL_dalpha = 0.0f;
-#pragma unroll
-					for (int ch = 0; ch < 3; ch++) {
-						const float c = col[ch];
-						accum_rec[p][ch] = last_alpha[p] * last_color[p][ch] + (1.f - last_alpha[p]) * accum_rec[p][ch];
-						last_color[p][ch] = c;
-						const float dL_dchannel = dL_dpixel[p][ch];
-						dL_dalpha += (c - accum_rec[p][ch]) * dL_dchannel;
-						v[6 + ch] += dchannel_dcolor * dL_dchannel;
-					}
-					dL_dalpha *= T[p];
+					const float aT = alpha[p] * T[p];
+					const float cdot = q2.x * dL_dpixel[p][0] + q2.y * dL_dpixel[p][1] + q2.z * dL_dpixel[p][2];
+					acc_dot[p] = last_alpha[p] * last_cdot[p] + (1.f - last_alpha[p]) * acc_dot[p];
+					last_cdot[p] = cdot;
+					float dL_dalpha = (cdot - acc_dot[p]) * T[p];
 					last_alpha[p] = alpha[p];
 					// background term (reference backward.cu:512-516); with a black background it adds (-x) * 0 = -0: skipped
 					if (has_bg) dL_dalpha += (-T_final[p] / (1.f - alpha[p])) * bg_dot_dpixel[p];
-
-					const float dL_dG = con_o.w * dL_dalpha;
-					const float gdx = G_[p] * d[p].x;
-					const float gdy = G_[p] * d[p].y;
-					const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
-					const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
-					v[0] += dL_dG * dG_ddelx * ddelx_dx;
-					v[1] += dL_dG * dG_ddely * ddely_dy;
-					v[2] += -0.5f * gdx * d[p].x * dL_dG;
-					v[3] += -0.5f * gdx * d[p].y * dL_dG;
-					v[4] += -0.5f * gdy * d[p].y * dL_dG;
-					v[5] += G_[p] * dL_dalpha;
+					vc0 += aT * dL_dpixel[p][0];
+					vc1 += aT * dL_dpixel[p][1];
+					vc2 += aT * dL_dpixel[p][2];
+					const float w = (con_o.w * dL_dalpha) * G_[p];
+					const float wy = w * d[p].y;
+					W0 += w;
+					Wy += wy;
+					Wyy += wy * d[p].y;
 				}
+				const float dx = d[0].x, Wx = W0 * dx;
+				const float v[9] = {W0, Wx, Wy, Wx * dx, Wy * dx, Wyy, vc0, vc1, vc2};
 				const float tot = warp_reduce9(v, lane);
 				// each (warp, entry) pair is visited once per batch: plain stores, no shared-memory atomics
-				if (my_slot >= 0) sm.acc[j * ACC_ROW + warp * 9 + my_slot] = tot;
-				if (lane == 0) dirty8[j * 8 + warp] = 1;
+				if (my_slot >= 0) sm.acc[j * ACC_ROW + warp * 10 + my_slot] = (lane == 1) ? 1.f : tot;
 			}
 		}
 		__syncthreads();
 
 		// one set of global reductions per (Gaussian, tile)
 		if (tid < cnt) {
-			const unsigned long long dm = sm.dirty[tid];
-			if (dm) {
-				sm.dirty[tid] = 0ull;
-				float a[9];
+			float a[9];
 #pragma unroll
-				for (int i = 0; i < 9; i++) a[i] = 0.f;
+			for (int i = 0; i < 9; i++) a[i] = 0.f;
+			bool any_w = false;
 #pragma unroll
-				for (int w = 0; w < G::NWARPS; w++) {
-					if ((dm >> (8 * w)) & 0xffull) {
+			for (int w = 0; w < G::NWARPS; w++) {
+				float* row = &sm.acc[tid * ACC_ROW + w * 10];
+				if (row[9] != 0.f) {
+					row[9] = 0.f;
+					any_w = true;
 #pragma unroll
-						for (int i = 0; i < 9; i++) a[i] += sm.acc[tid * ACC_ROW + w * 9 + i];
-					}
+					for (int i = 0; i < 9; i++) a[i] += row[i];
+				}
+			}
+			if (any_w) {
+				{   // moments -> the reference's nine sums
+					const float4 q0 = sm.rec[st][tid].q0, q1 = sm.rec[st][tid].q1;
+					const float A = q0.z, B = q0.w, C = q1.x, M0 = a[0], Mx = a[1], My = a[2], Mxx = a[3], Mxy = a[4], Myy = a[5];
+					a[0] = -(A * Mx + B * My) * ddelx_dx;
+					a[1] = -(C * My + B * Mx) * ddely_dy;
+					a[2] = -0.5f * Mxx;
+					a[3] = -0.5f * Mxy;
+					a[4] = -0.5f * Myy;
+					a[5] = M0 / q1.y;
 				}
 				const uint32_t g = sm.gid[st][tid];
 				if (sink.packed) {

@@ -131,3 +131,97 @@ def test_stereo_vision_kernels_through_the_libtorch_shim(cuda):
     m = torch.eye(4, device=cuda).flatten().contiguous()
     m[12:15] = torch.tensor([1.0, 2.0, 3.0], device=cuda)
     assert torch.allclose(torch.ops.psb200.transform_points(pts.clone(), m), pts + torch.tensor([1.0, 2.0, 3.0], device=cuda))
+
+
+def _ref_points_ops():
+    """torch.ops.psbref.*: the reference's OWN src/operate_points.cu / src/stereo_vision.cu kernels (compiled unmodified, oracle/Makefile
+    target refpoints; façade oracle/ref_points_shim.cpp)."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "oracle", "_ref", "libref_points.so")
+    if not os.path.exists(lib):
+        pytest.skip("oracle/_ref/libref_points.so not built (make -C oracle refpoints where /root/reference exists)")
+    torch.ops.load_library(lib)
+    return torch.ops.psbref
+
+
+def test_point_operators_pinned_to_the_reference_kernels(cuda):
+    """psb_transform_points / psb_scale_transform_points / markVisible against the reference's own kernels on the same inputs:
+    transformPoints and scaleAndTransformThenMarkVisiblePoints (reference src/operate_points.cu:38-143, incl. the quaternion write
+    quirk of cuda_rasterizer/operate_points.h:170-178, which fix_quaternion_write=False reproduces)."""
+    import photo_slam_b200.synthetic as syn
+    from photo_slam_b200 import points
+    ref = _ref_points_ops()
+    rng = np.random.default_rng(5)
+    P = 40_003
+    R, t = syn.random_pose(rng, 1.0, 2.0)
+    M = np.eye(4)
+    M[:3, :3], M[:3, 3] = R, t
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    m_flat = T(M.T.reshape(-1).astype(np.float32))
+    pts = T(rng.normal(size=(P, 3)).astype(np.float32) * 3)
+    rots = rng.normal(size=(P, 4)).astype(np.float32)
+    rots = T(rots / np.linalg.norm(rots, axis=1, keepdims=True))
+    a = points.transformPoints(pts.clone(), m_flat)
+    b = ref.transform_points(pts.clone(), m_flat.view(4, 4))
+    assert torch.allclose(a, b, rtol=1e-6, atol=1e-6) and (a - b).abs().max().item() < 1e-5
+    cam = syn.make_camera(640, 480, 500.0, 500.0)
+    ntm, unstable = T(rng.random(P) > 0.3), T(rng.random(P) > 0.2)
+    view, proj = T(cam["viewmatrix"]), T(cam["projmatrix"])
+    pa, ra, ma = pts.clone(), rots.clone(), ntm.clone()
+    na = points.scaleAndTransformThenMarkVisiblePoints(pa, ra, ma, unstable, m_flat, view, proj, 3, scale=1.3, fix_quaternion_write=False)
+    pb, rb, mb, nb = ref.scale_transform_mark_visible(pts.clone(), rots.clone(), ntm.clone(), unstable, m_flat.view(4, 4), view.view(4, 4), proj.view(4, 4), 3, 1.3)
+    torch.cuda.synchronize()
+    assert na == nb and torch.equal(ma, mb)
+    assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-5)
+    assert torch.allclose(ra, rb, rtol=1e-5, atol=1e-6), (ra - rb).abs().max().item()
+
+
+def test_stereo_vision_kernels_pinned_to_the_reference_kernels(cuda):
+    """psb_reproject_depth_pinhole / psb_neighbour_depth_pinhole against reprojectDepthPinhole /
+    monocularPinholeInactiveGeoDensifyBySearchingNeighborhoodKeypoints of reference src/stereo_vision.cu:39-215 (own kernels, compiled unmodified)."""
+    import os
+    from photo_slam_b200 import _lib
+    ref = _ref_points_ops()
+    shim = os.path.join(os.path.dirname(_lib.LIB_PATH), "libcuda_rasterizer.so")
+    if not os.path.exists(shim):
+        pytest.skip("libcuda_rasterizer.so not built")
+    torch.ops.load_library(shim)
+    rng = np.random.default_rng(11)
+    W, H = 160, 120
+    fx, fy, cx, cy = 150.0, 151.0, 79.5, 59.5
+    depth = torch.from_numpy(rng.uniform(0.5, 5.0, W * H).astype(np.float32)).to(cuda)
+    mask = torch.from_numpy(rng.random(W * H) > 0.4).to(cuda)
+    a = torch.ops.psb200.reproject_depth_pinhole(depth, mask, fx, fy, cx, cy, W)
+    b = ref.reproject_depth_pinhole(depth, mask, [fx, fy, cx, cy], W)
+    assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)
+    N = 3000
+    px = torch.from_numpy(np.stack([rng.integers(0, W, N), rng.integers(0, H, N)], 1).astype(np.float32)).to(cuda)
+    has3d = torch.from_numpy(rng.random(N) > 0.5).to(cuda)
+    pl = torch.from_numpy(rng.uniform(0.5, 4.0, (N, 3)).astype(np.float32)).to(cuda)
+    colors = torch.from_numpy(rng.random(W * H * 3 + 8).astype(np.float32)).to(cuda)
+    pa, ca = torch.ops.psb200.neighbour_depth_pinhole(px, has3d, pl, colors, 40.0, fx, fy, cx, cy, W)
+    pb, cb = ref.neighbour_depth_pinhole(px, has3d, pl, colors, 40.0, [fx, fy, cx, cy], W)
+    assert pa.shape == pb.shape and pa.shape[0] > N // 2
+    assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-6) and torch.equal(ca, cb)
+
+
+def test_dist_cuda2_large_and_clustered(cuda):
+    """The block-cooperative 3-NN search on a large, strongly non-uniform cloud (tight clusters + sparse background + duplicates) against
+    the reference simple-knn build."""
+    import time
+    import ref_gpu
+    from photo_slam_b200 import points
+    if not ref_gpu.available():
+        pytest.skip("oracle/_ref not built")
+    gen = torch.Generator(device=cuda).manual_seed(3)
+    centres = torch.randn((40, 3), device=cuda, generator=gen) * 5
+    pts = torch.cat([centres[torch.randint(0, 40, (200_000,), device=cuda, generator=gen)] + 0.01 * torch.randn((200_000, 3), device=cuda, generator=gen),
+                     torch.randn((50_001, 3), device=cuda, generator=gen) * 20], dim=0)
+    pts[::11] = pts[1::11][: pts[::11].shape[0]]
+    a = points.distCUDA2(pts)
+    torch.cuda.synchronize()
+    t0 = time.time(); a = points.distCUDA2(pts); torch.cuda.synchronize(); t1 = time.time()
+    b = ref_gpu.dist_cuda2(pts); torch.cuda.synchronize(); t2 = time.time()
+    print(f"distCUDA2 over {pts.shape[0]} points: psb200 {1e3 * (t1 - t0):.2f} ms, reference simple-knn {1e3 * (t2 - t1):.2f} ms")
+    assert torch.allclose(a, b, rtol=1e-6, atol=0)
