@@ -267,8 +267,11 @@ __global__ void __launch_bounds__(TB, PSB_A_MINBLOCKS) gaussian_backward_kernel(
 		for (int i = tid; i < rows * (SEED / 4); i += TB) {
 			if (__float_as_uint(s_w[i / (SEED / 4)][19]) == dp.epoch) dst[i] = src[i];
 		}
-		// "all my records of this step have landed": every thread fences its own remote stores, the last block of the grid
-		// publishes this rank's camera centre and then the epoch flag on every rank (threadFenceReduction pattern)
+		// "all my records of this step have landed". Default: nothing here — dp_signal_kernel, queued right behind this kernel,
+		// publishes the camera centre and raises the flags after ONE system-scope fence (the kernel boundary orders it after every
+		// store of this grid). PSB_DP_SIGNAL=fence: every thread fences its own remote stores, the last block of the grid publishes
+		// (threadFenceReduction pattern) — measured slower: a system-scope fence per block costs microseconds with NVLink stores in flight.
+		if (!dp.fence_in_kernel) return;
 		__threadfence_system();
 		__syncthreads();
 		if (tid == 0) {
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(TB) shard_adam_small_kernel(DpShard d, TrainTe
 	float4* dst = reinterpret_cast<float4*>(d.g_rest + (size_t)lc * (TB * REST));
 	const float4* src = reinterpret_cast<const float4*>(s_g);
 	for (int i = tid; i < TB * REST / 4; i += TB) dst[i] = src[i];
-	__threadfence_system();  // this block's remote stores are performed before the kernel can complete
+	if (d.fence_in_kernel) __threadfence_system();  // this block's remote stores are performed before the kernel can complete
 }
 
 // Adam over the f_rest rows of the owned chunks, one block per chunk (5760 floats), 128-bit accesses; the updated values go
@@ -501,7 +504,8 @@ __global__ void __launch_bounds__(256) shard_adam_frest_kernel(DpShard d, TrainT
 			}
 		}
 	}
-	// "my updated rows have landed everywhere": last block of the grid raises this rank's flag on every rank
+	// "my updated rows have landed everywhere": dp_signal_kernel behind this kernel (default), or the last block of the grid
+	if (!d.fence_in_kernel) return;
 	__threadfence_system();
 	__syncthreads();
 	if (threadIdx.x == 0) {
@@ -512,6 +516,28 @@ __global__ void __launch_bounds__(256) shard_adam_frest_kernel(DpShard d, TrainT
 			for (int j = 0; j < d.world; j++) *reinterpret_cast<volatile uint32_t*>(d.param_flag[j] + d.rank) = d.epoch;
 		}
 	}
+}
+
+// One warp, queued right behind a data kernel of the data-parallel step: lane j publishes (optionally) this rank's meta row and then
+// raises this rank's epoch word on rank j. Stream order puts it after every store of the data kernel; the single system-scope fence
+// orders those stores (cumulativity) before the flag for an observer on another GPU.
+struct DpSignal {
+	uint32_t* flag[DP_MAX_WORLD];
+	float* meta[DP_MAX_WORLD];   // null: no meta row
+	const float* campos;
+	int world, rank, degree;
+	uint32_t epoch;
+};
+__global__ void dp_signal_kernel(DpSignal s)
+{
+	const int j = threadIdx.x;
+	if (j < s.world && s.meta[j]) {
+		float* mt = s.meta[j] + 8 * s.rank;
+		mt[0] = s.campos[0]; mt[1] = s.campos[1]; mt[2] = s.campos[2]; mt[3] = (float)s.degree;
+	}
+	__threadfence_system();
+	__syncwarp();
+	if (j < s.world) *reinterpret_cast<volatile uint32_t*>(s.flag[j] + s.rank) = s.epoch;
 }
 
 __device__ __forceinline__ unsigned long long global_timer_ns()
@@ -573,6 +599,14 @@ int launch_push_backward(int P, const TrainTensors& t, const Camera& cam, const 
 	gaussian_backward_kernel<MODE_PUSH><<<cdiv(P, TB), TB, 0, stream>>>(0, P, t, cam, geom, reinterpret_cast<float4*>(sink), h, nog, st, counters, capacity,
 	                                                                  nullptr, dp);
 	PSB_LAUNCH_OK();
+	if (!dp.fence_in_kernel) {
+		DpSignal s;
+		memset(&s, 0, sizeof(s));
+		for (int j = 0; j < dp.world; j++) { s.flag[j] = dp.grad_flag[j]; s.meta[j] = dp.meta[j]; }
+		s.campos = cam.campos; s.world = dp.world; s.rank = dp.rank; s.degree = h.D; s.epoch = dp.epoch;
+		dp_signal_kernel<<<1, 32, 0, stream>>>(s);
+		PSB_LAUNCH_OK();
+	}
 	return 0;
 }
 
@@ -585,6 +619,14 @@ int launch_shard_adam(const DpShard& d, const TrainTensors& t, const StepHyper& 
 	PSB_LAUNCH_OK();
 	shard_adam_frest_kernel<<<d.nlocal, 256, 0, stream>>>(d, t, h.lr[2] * ac.inv_bc1, ac);
 	PSB_LAUNCH_OK();
+	if (!d.fence_in_kernel) {
+		DpSignal s;
+		memset(&s, 0, sizeof(s));
+		for (int j = 0; j < d.world; j++) s.flag[j] = d.param_flag[j];
+		s.world = d.world; s.rank = d.rank; s.epoch = d.epoch;
+		dp_signal_kernel<<<1, 32, 0, stream>>>(s);
+		PSB_LAUNCH_OK();
+	}
 	return 0;
 }
 

@@ -42,6 +42,8 @@ struct DpPush {              // what the per-Gaussian backward needs to deliver 
 	uint32_t* done_counter;            // local
 	int world, rank, nlocal_max;
 	uint32_t epoch;
+	int fence_in_kernel;               // 1: every block fences its remote stores, the grid's last block raises the flags (PSB_DP_SIGNAL=fence)
+	                                   // 0: a one-block signal kernel behind the data kernel does (stream order + ONE system fence; default)
 };
 struct DpShard {             // what the owner-side Adam kernels need
 	float* param[DP_MAX_WORLD][6];     // the six parameter tensors on every rank (row of `rank` = local)
@@ -52,6 +54,7 @@ struct DpShard {             // what the owner-side Adam kernels need
 	uint32_t* done_counter;            // local
 	int world, rank, nlocal_max, nlocal, P;
 	uint32_t epoch;
+	int fence_in_kernel;               // as in DpPush
 };
 int launch_push_backward(int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, const StepHyper& h,
                          const DensifyStats& st, const uint32_t* counters, uint32_t capacity, const DpPush& dp, cudaStream_t stream);

@@ -392,6 +392,8 @@ int psb_dp_step(psb_trainer* t, psb_dp* d, int P, int M, const psb_model* model,
 		for (int i = 0; i < 6; i++) sh.param[j][i] = reinterpret_cast<float*>(d->peer[j] + d->off_param[i]);
 	}
 	push.done_counter = d->local; push.world = d->world; push.rank = d->rank; push.nlocal_max = d->nlocal_max; push.epoch = epoch;
+	static const int fence_in_kernel = (getenv("PSB_DP_SIGNAL") && strcmp(getenv("PSB_DP_SIGNAL"), "fence") == 0) ? 1 : 0;
+	push.fence_in_kernel = fence_in_kernel; sh.fence_in_kernel = fence_in_kernel;
 	// per-Gaussian backward; its 80-byte records go straight into the owners' inboxes
 	if ((rc = launch_push_backward(P, tt, cam, geom, t->sink, h, st, geom.counters, (uint32_t)t->capacity, push, stream))) return rc;
 	t->mark(7, stream);
