@@ -342,7 +342,7 @@ def run_psb(args, world, rank, local, dev):
         peak_src = "MEASURED_PEAKS.json hbm_gbs"
     except Exception:
         pass
-    if world > 1:
+    if world > 1 and dp_mode == "p2p":
         rewind()
         tr.set_profiling(True)
         acc = {}

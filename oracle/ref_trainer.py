@@ -96,6 +96,28 @@ class RefTrainer:
         color, radii = _RefRasterize.apply(self.xyz, screenspace_points, shs, e, opacity, scales, rotations, e, rs)
         return color, screenspace_points, radii > 0, radii
 
+    def densify_and_prune(self, max_grad, min_opacity, extent, max_screen_size, percent_dense=0.01, z=None):
+        """GaussianModel::densifyAndPrune (reference src/gaussian_model.cpp:795-815) on this trainer's tensors and torch.optim.Adam state,
+        through the ATen restatement oracle/ref_densify.py (tensor surgery + optimizer-state surgery like :588-714). z: optional injected
+        standard-normal draw for the split (else torch.randn)."""
+        import ref_densify
+        ps = self.tensors()
+        zeros = lambda t: torch.zeros_like(t)
+        stt = [self.optimizer.state.get(p, {}) for p in ps]
+        st = dict(p=[p.detach() for p in ps], m=[s.get("exp_avg", zeros(p)).detach() for s, p in zip(stt, ps)],
+                  v=[s.get("exp_avg_sq", zeros(p)).detach() for s, p in zip(stt, ps)], accum=self.xyz_gradient_accum, denom=self.denom,
+                  max_radii=self.max_radii2D)
+        steps = [s.get("step", torch.tensor(0.0)) for s in stt]
+        lrs = [g["lr"] for g in self.optimizer.param_groups]
+        ref_densify.densify_and_prune(st, max_grad, min_opacity, extent, max_screen_size, percent_dense, z)
+        new = [t.contiguous().clone().requires_grad_(True) for t in st["p"]]
+        self.xyz, self.f_dc, self.f_rest, self.opacity, self.scaling, self.rotation = new
+        self.optimizer = torch.optim.Adam([{"params": [p], "lr": lr} for p, lr in zip(new, lrs)], lr=0.0, eps=1e-15, foreach=False, fused=False)
+        for p, m, v, stp in zip(new, st["m"], st["v"], steps):
+            self.optimizer.state[p] = {"step": stp.clone() if torch.is_tensor(stp) else torch.tensor(float(stp)), "exp_avg": m.contiguous().clone(),
+                                       "exp_avg_sq": v.contiguous().clone()}
+        self.max_radii2D, self.xyz_gradient_accum, self.denom = st["max_radii"], st["accum"], st["denom"]
+
     def train_for_one_iteration(self, cam, gt_image, mask=None, densify_stats=True, sync=True):
         image, viewspace, visibility_filter, radii = self.render(cam)
         masked = image * mask if mask is not None else image

@@ -312,8 +312,12 @@ __global__ void __launch_bounds__(256) frest_stream_kernel(uint32_t e_first, uin
 	}
 	if (e + 4 <= e_end) {
 		if (ADAM) {
-			float4 pp = __ldcs(reinterpret_cast<const float4*>(p + e)), mm = __ldcs(reinterpret_cast<const float4*>(m + e)),
-			       vv = __ldcs(reinterpret_cast<const float4*>(v + e));
+			float4 mm = __ldcs(reinterpret_cast<const float4*>(m + e)), vv = __ldcs(reinterpret_cast<const float4*>(v + e));
+			// a zero gradient on zero moments is an exact no-op of Adam (m' = v' = 0, p' = p - lr * 0 / (0 + eps) = p): such elements
+			// (Gaussians no view has reached since their moments were created) are neither re-read nor rewritten
+			if (g[0] == 0.f && g[1] == 0.f && g[2] == 0.f && g[3] == 0.f && mm.x == 0.f && mm.y == 0.f && mm.z == 0.f && mm.w == 0.f &&
+			    vv.x == 0.f && vv.y == 0.f && vv.z == 0.f && vv.w == 0.f) return;
+			float4 pp = __ldcs(reinterpret_cast<const float4*>(p + e));
 			adam1(pp.x, mm.x, vv.x, g[0], lr_eff, ac);
 			adam1(pp.y, mm.y, vv.y, g[1], lr_eff, ac);
 			adam1(pp.z, mm.z, vv.z, g[2], lr_eff, ac);
