@@ -285,40 +285,28 @@ def run_psb(args, world, rank, local, dev):
     # --- e2e: the call a user makes (GaussianTrainer.trainHost): pinned HOST buffers in (ground-truth image + camera,
     #     copied to the device every step inside the timed region), the step's loss read back to the host every step
     #     (through the trainer's early read-back event); flushHost() drains the last backward inside the timed region
-    if world == 1:
-        hostcam = dict(devcam, viewmatrix=host["viewmatrix"], projmatrix=host["projmatrix"], campos=host["campos"])
-        rewind()
-        for _ in range(3):
-            tr.trainHost(hostcam, host["gt"])
-        tr.flushHost()
-        rewind()
-        barrier(world)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        losses = []
-        for _ in range(args.steps):
-            losses.append(tr.trainHost(hostcam, host["gt"]))
-        tr.flushHost()
-        e1.record()
-        barrier(world)
-        loss_host = losses[-1]
-        assert len(losses) == args.steps and all(l is not None for l in losses)
-    else:
-        stage = dict(gt=torch.empty_like(gt_dev), viewmatrix=torch.empty_like(devcam["viewmatrix"]), projmatrix=torch.empty_like(devcam["projmatrix"]),
-                     campos=torch.empty_like(devcam["campos"]))
-        cam2 = dict(devcam, viewmatrix=stage["viewmatrix"], projmatrix=stage["projmatrix"], campos=stage["campos"])
-        rewind()
-        barrier(world)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            for k in ("gt", "viewmatrix", "projmatrix", "campos"):
-                stage[k].copy_(host[k], non_blocking=True)
-            tr.trainForOneIteration(cam2, stage["gt"])
-            loss_host = tr.result()[0]          # device -> host read of the step's loss (blocks, like loss.item())
-        tr.sync()
-        e1.record()
-        barrier(world)
+    # (same front end at every N: the data-parallel trainer overrides the step, not the host input path)
+    hostcam = dict(devcam, viewmatrix=host["viewmatrix"], projmatrix=host["projmatrix"], campos=host["campos"])
+    rewind()
+    for _ in range(3):
+        tr.trainHost(hostcam, host["gt"])
+    tr.flushHost()
+    rewind()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    losses = []
+    for _ in range(args.steps):
+        losses.append(tr.trainHost(hostcam, host["gt"]))
+    if world > 1:
+        tr.sync()                    # every rank's rows of the last step have landed (device-side wait, inside the timed region)
+    tr.flushHost()
+    e1.record()
+    barrier(world)
+    loss_host = losses[-1]
+    assert len(losses) == args.steps and all(l is not None for l in losses)
+    if world > 1:
+        assert tr.dropped_views == 0 and tr.status() == 0
     ms_e2e = max_over_ranks(e0.elapsed_time(e1), world, dev) / args.steps
     h2d = sum(host[k].numel() * 4 for k in ("gt", "viewmatrix", "projmatrix", "campos"))
 
@@ -377,7 +365,7 @@ def run_psb(args, world, rank, local, dev):
             if k in SINGLE_KERNEL_STAGES:
                 pr = prof.get(STAGE_KERNELS[k][0])
                 if pr:   # ncu capture of the same kernels (cold-cache, serialised): DRAM traffic and warp instructions per launch
-                    row["ncu_dram_GB"] = float(pr[0]["dram_rd [Gbyte]"]) + float(pr[0]["dram_wr [Gbyte]"])
+                    row["ncu_dram_GB"] = (float(pr[0]["dram_rd [byte]"]) + float(pr[0]["dram_wr [byte]"])) / 1e9   # tools/ncu_summary.py: base units
                     row["ncu_warp_inst"] = float(pr[0]["warp_inst [inst]"])
                     # issue roofline: warp instructions / (148 SMs x 4 schedulers x SM clock x time) — the ceiling that binds the tile kernels
                     row["issue_frac"] = row["ncu_warp_inst"] / (148 * 4 * sm_clock_ghz * 1e9 * stages[k] * 1e-3)

@@ -384,7 +384,7 @@ __device__ __forceinline__ void sh_weights(int deg, const float3 pos, const floa
 __global__ void __launch_bounds__(TB) shard_adam_small_kernel(DpShard d, TrainTensors t, StepHyper h, float grad_scale)
 {
 	__shared__ __align__(16) float s_g[TB * REST];
-	const int tid = threadIdx.x, lc = blockIdx.x;
+	const int tid = threadIdx.x, lc = d.lc_first + blockIdx.x;
 	const int chunk = lc * d.world + d.rank;
 	const int idx = chunk * TB + tid;
 	const bool valid = idx < d.P;
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(TB) shard_adam_small_kernel(DpShard d, TrainTe
 // to every rank. Rows nobody has ever seen (g = m = v = 0) are left alone: their Adam update is exactly zero.
 __global__ void __launch_bounds__(256) shard_adam_frest_kernel(DpShard d, TrainTensors t, float lr_eff, AdamCoef ac)
 {
-	const int lc = blockIdx.x;
+	const int lc = d.lc_first + blockIdx.x;
 	const int chunk = lc * d.world + d.rank;
 	const size_t e0 = (size_t)chunk * (TB * REST);
 	const size_t e_end = (size_t)d.P * REST;
@@ -555,7 +555,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 // process) must not hang this GPU — after timeout_ns the kernel records the failure and returns.
 __global__ void wait_flags_kernel(const uint32_t* flags, int world, uint32_t epoch, uint32_t* status, unsigned long long timeout_ns)
 {
-	const int lane = threadIdx.x;
+	const int lane = threadIdx.x;   // `world` = number of flag words (ranks, or groups x ranks), <= blockDim.x
 	if (lane >= world) return;
 	const volatile uint32_t* f = flags + lane;
 	const unsigned long long t0 = global_timer_ns();
@@ -594,15 +594,16 @@ int launch_fused_backward(bool adam, int first, int P, const TrainTensors& t, co
 	return 0;
 }
 
-int launch_push_backward(int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, const StepHyper& h,
+int launch_push_backward(int first, int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, const StepHyper& h,
                          const DensifyStats& st, const uint32_t* counters, uint32_t capacity, const DpPush& dp, cudaStream_t stream)
 {
-	if (P <= 0) return 0;
 	GradSegments nog;
 	memset(&nog, 0, sizeof(nog));
-	gaussian_backward_kernel<MODE_PUSH><<<cdiv(P, TB), TB, 0, stream>>>(0, P, t, cam, geom, reinterpret_cast<float4*>(sink), h, nog, st, counters, capacity,
-	                                                                  nullptr, dp);
-	PSB_LAUNCH_OK();
+	if (P - first > 0) {  // Gaussians [first, P): one pipeline group (first is a multiple of 128 * world)
+		gaussian_backward_kernel<MODE_PUSH><<<cdiv(P - first, TB), TB, 0, stream>>>(first, P, t, cam, geom, reinterpret_cast<float4*>(sink), h, nog, st, counters,
+		                                                                          capacity, nullptr, dp);
+		PSB_LAUNCH_OK();
+	}
 	if (!dp.fence_in_kernel) {
 		DpSignal s;
 		memset(&s, 0, sizeof(s));
@@ -616,13 +617,14 @@ int launch_push_backward(int P, const TrainTensors& t, const Camera& cam, const 
 
 int launch_shard_adam(const DpShard& d, const TrainTensors& t, const StepHyper& h, float grad_scale, cudaStream_t stream)
 {
-	if (d.nlocal <= 0) return 0;
 	AdamCoef ac;
 	ac.beta1 = h.beta1; ac.beta2 = h.beta2; ac.eps = h.eps; ac.inv_bc1 = h.inv_bc1; ac.inv_bc2_sqrt = 1.0f / h.bc2_sqrt;
-	shard_adam_small_kernel<<<d.nlocal, TB, 0, stream>>>(d, t, h, grad_scale);
-	PSB_LAUNCH_OK();
-	shard_adam_frest_kernel<<<d.nlocal, 256, 0, stream>>>(d, t, h.lr[2] * ac.inv_bc1, ac);
-	PSB_LAUNCH_OK();
+	if (d.nlocal > 0) {  // owned chunks [lc_first, lc_first + nlocal) of this pipeline group
+		shard_adam_small_kernel<<<d.nlocal, TB, 0, stream>>>(d, t, h, grad_scale);
+		PSB_LAUNCH_OK();
+		shard_adam_frest_kernel<<<d.nlocal, 256, 0, stream>>>(d, t, h.lr[2] * ac.inv_bc1, ac);
+		PSB_LAUNCH_OK();
+	}
 	if (!d.fence_in_kernel) {
 		DpSignal s;
 		memset(&s, 0, sizeof(s));
@@ -637,7 +639,7 @@ int launch_shard_adam(const DpShard& d, const TrainTensors& t, const StepHyper& 
 int launch_wait_flags(const uint32_t* flags, int world, uint32_t epoch, uint32_t* status, cudaStream_t stream)
 {
 	static const unsigned long long timeout_ns = (unsigned long long)(getenv("PSB_DP_TIMEOUT_MS") ? atoll(getenv("PSB_DP_TIMEOUT_MS")) : 20000) * 1000000ull;
-	wait_flags_kernel<<<1, 32, 0, stream>>>(flags, world, epoch, status, timeout_ns);
+	wait_flags_kernel<<<1, world <= 32 ? 32 : 64, 0, stream>>>(flags, world, epoch, status, timeout_ns);
 	PSB_LAUNCH_OK();
 	return 0;
 }

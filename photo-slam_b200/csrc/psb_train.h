@@ -52,14 +52,15 @@ struct DpShard {             // what the owner-side Adam kernels need
 	const float* meta;                 // local meta rows
 	float* g_rest;                     // local scratch [nlocal_max*128][45]: summed f_rest gradient of the owned rows
 	uint32_t* done_counter;            // local
-	int world, rank, nlocal_max, nlocal, P;
+	int world, rank, nlocal_max, nlocal, P;   // nlocal: owned chunks handled by this launch, starting at local chunk lc_first
+	int lc_first;
 	uint32_t epoch;
 	int fence_in_kernel;               // as in DpPush
 };
-int launch_push_backward(int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, const StepHyper& h,
+int launch_push_backward(int first, int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, const StepHyper& h,
                          const DensifyStats& st, const uint32_t* counters, uint32_t capacity, const DpPush& dp, cudaStream_t stream);
 int launch_shard_adam(const DpShard& d, const TrainTensors& t, const StepHyper& h, float grad_scale, cudaStream_t stream);
-// spins (device side, one warp) until flags[0..world) >= epoch; after `timeout_ms` writes 1 to *status and gives up
+// spins (device side) until flags[0..world) >= epoch (world <= 64 words); after `timeout_ms` writes 1 to *status and gives up
 int launch_wait_flags(const uint32_t* flags, int world, uint32_t epoch, uint32_t* status, cudaStream_t stream);
 
 // Gaussians [first, P) (first must be a multiple of 128 so f_rest chunks stay 16-byte aligned)

@@ -245,6 +245,10 @@ struct psb_dp {
 	uint32_t epoch = 0;
 	bool connected = false;
 	cudaIpcMemHandle_t handle;
+	// pipeline: the Gaussians are cut into `groups` contiguous ranges (boundaries at multiples of 128 * world chunks); the owner-side Adam
+	// of group g runs on `adam_stream` as soon as every rank's records of group g have landed, under the push backward of group g + 1
+	int groups = 1, chunks_per_group = 0;
+	cudaStream_t adam_stream = nullptr;
 };
 
 namespace {
@@ -272,12 +276,24 @@ int psb_dp_create(psb_dp** out, int rank, int world, int P)
 	d->nlocal_max = (d->nchunks + world - 1) / world;
 	d->nlocal = d->nchunks > rank ? (d->nchunks - rank + world - 1) / world : 0;
 	dp_layout(d);
+	{
+		const char* g = getenv("PSB_DP_GROUPS");
+		int G = g ? atoi(g) : 4;
+		if (getenv("PSB_DP_SIGNAL") && strcmp(getenv("PSB_DP_SIGNAL"), "fence") == 0) G = 1;   // the in-kernel signalling variant is not pipelined
+		G = G < 1 ? 1 : (G > 8 ? 8 : G);
+		int cpg = (d->nchunks + G - 1) / G;
+		cpg = (cpg + world - 1) / world * world;          // a group holds whole rounds of the chunk -> owner rotation
+		if (cpg < world) cpg = world;
+		d->chunks_per_group = cpg;
+		d->groups = d->nchunks > 0 ? (d->nchunks + cpg - 1) / cpg : 1;
+	}
 	cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d->base), d->bytes);
 	if (e == cudaSuccess) e = cudaMemset(d->base, 0, d->bytes);
 	if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d->g_rest), ((size_t)d->nlocal_max * 128 * 45 + 64) * sizeof(float));
 	if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d->local), 8 * sizeof(uint32_t));
 	if (e == cudaSuccess) e = cudaMemset(d->local, 0, 8 * sizeof(uint32_t));
 	if (e == cudaSuccess && world > 1) e = cudaIpcGetMemHandle(&d->handle, d->base);
+	if (e == cudaSuccess && d->groups > 1) e = cudaStreamCreateWithFlags(&d->adam_stream, cudaStreamNonBlocking);
 	if (e != cudaSuccess) {
 		set_error("psb_dp_create", e, __FILE__, __LINE__);
 		cudaFree(d->base); cudaFree(d->g_rest); cudaFree(d->local);
@@ -328,6 +344,7 @@ int psb_dp_destroy(psb_dp* d)
 	for (int j = 0; j < d->world; j++)
 		if (j != d->rank && d->peer[j]) cudaIpcCloseMemHandle(d->peer[j]);
 	cudaFree(d->base); cudaFree(d->g_rest); cudaFree(d->local);
+	if (d->adam_stream) cudaStreamDestroy(d->adam_stream);
 	delete d;
 	return 0;
 }
@@ -337,8 +354,8 @@ int psb_dp_destroy(psb_dp* d)
 int psb_dp_sync(psb_dp* d, void* stream_)
 {
 	if (!d) { set_error_msg("psb_dp_sync: null"); return PSB_ERR_ARG; }
-	if (d->epoch == 0 || d->world == 1) return 0;
-	return launch_wait_flags(reinterpret_cast<const uint32_t*>(d->base + d->off_pflag), d->world, d->epoch, d->local + 2, (cudaStream_t)stream_);
+	if (d->epoch == 0 || (d->world == 1 && d->groups == 1)) return 0;   // (one rank, one group: everything is on the caller's stream)
+	return launch_wait_flags(reinterpret_cast<const uint32_t*>(d->base + d->off_pflag), d->groups * d->world, d->epoch, d->local + 2, (cudaStream_t)stream_);
 }
 
 // 0 = healthy, 1 = a cross-rank wait timed out (a peer never arrived); synchronises the stream
@@ -366,8 +383,8 @@ int psb_dp_step(psb_trainer* t, psb_dp* d, int P, int M, const psb_model* model,
 	const uint32_t epoch = ++d->epoch;
 	t->mark(psb_trainer::NSTAGE, stream);
 	// every rank's updated rows of the previous step must have landed here before this step reads the parameters
-	if (epoch > 1 && d->world > 1)
-		if ((rc = launch_wait_flags(reinterpret_cast<const uint32_t*>(d->base + d->off_pflag), d->world, epoch - 1, d->local + 2, stream))) return rc;
+	if (epoch > 1 && (d->world > 1 || d->groups > 1))   // (also orders this step behind the previous step's work on the adam stream)
+		if ((rc = launch_wait_flags(reinterpret_cast<const uint32_t*>(d->base + d->off_pflag), d->groups * d->world, epoch - 1, d->local + 2, stream))) return rc;
 	// render, loss, tile backward (the 9 screen-space sums per Gaussian)
 	if ((rc = step_impl(t, P, M, model, camera, background, gt_image, mask, step, out_color, radii, nullptr, stream, /*tiles_only=*/true))) return rc;
 	if (P == 0) return 0;
@@ -394,18 +411,33 @@ int psb_dp_step(psb_trainer* t, psb_dp* d, int P, int M, const psb_model* model,
 	push.done_counter = d->local; push.world = d->world; push.rank = d->rank; push.nlocal_max = d->nlocal_max; push.epoch = epoch;
 	static const int fence_in_kernel = (getenv("PSB_DP_SIGNAL") && strcmp(getenv("PSB_DP_SIGNAL"), "fence") == 0) ? 1 : 0;
 	push.fence_in_kernel = fence_in_kernel; sh.fence_in_kernel = fence_in_kernel;
-	// per-Gaussian backward; its 80-byte records go straight into the owners' inboxes
-	if ((rc = launch_push_backward(P, tt, cam, geom, t->sink, h, st, geom.counters, (uint32_t)t->capacity, push, stream))) return rc;
-	t->mark(7, stream);
-	// every rank's records of this epoch have landed here
-	if ((rc = launch_wait_flags(reinterpret_cast<const uint32_t*>(d->base + d->off_gflag), d->world, epoch, d->local + 2, stream))) return rc;
-	t->mark(8, stream);
 	sh.inbox = reinterpret_cast<const float*>(d->base + d->off_inbox);
 	sh.meta = reinterpret_cast<const float*>(d->base + d->off_meta);
 	sh.g_rest = d->g_rest; sh.done_counter = d->local + 1;
-	sh.world = d->world; sh.rank = d->rank; sh.nlocal_max = d->nlocal_max; sh.nlocal = d->nlocal; sh.P = P; sh.epoch = epoch;
-	rc = launch_shard_adam(sh, tt, h, 1.0f / (float)d->world, stream);
-	t->mark(9, stream);
+	sh.world = d->world; sh.rank = d->rank; sh.nlocal_max = d->nlocal_max; sh.P = P; sh.epoch = epoch;
+	// Pipeline over groups of chunks: [main stream] push backward of group g (records go straight into the owners' inboxes) + signal;
+	// [adam stream] wait until every rank's records of group g have landed -> Adam of the owned rows of group g, updated rows stored to
+	// every replica + signal. With one group everything stays on the main stream. Flag word of (group g, rank r) = g * world + r.
+	cudaStream_t as = d->groups > 1 ? d->adam_stream : stream;
+	const int rows_per_group = d->chunks_per_group * 128;
+	for (int g = 0; g < d->groups; g++) {
+		DpPush pg = push;
+		for (int j = 0; j < d->world; j++) pg.grad_flag[j] = push.grad_flag[j] + g * d->world;
+		const int first = g * rows_per_group, last = (g + 1) * rows_per_group < P ? (g + 1) * rows_per_group : P;
+		if ((rc = launch_push_backward(first, last, tt, cam, geom, t->sink, h, st, geom.counters, (uint32_t)t->capacity, pg, stream))) return rc;
+	}
+	t->mark(7, stream);
+	t->mark(8, stream);
+	for (int g = 0; g < d->groups; g++) {
+		if ((rc = launch_wait_flags(reinterpret_cast<const uint32_t*>(d->base + d->off_gflag) + g * d->world, d->world, epoch, d->local + 2, as))) return rc;
+		DpShard sg = sh;
+		for (int j = 0; j < d->world; j++) sg.param_flag[j] = sh.param_flag[j] + g * d->world;
+		sg.lc_first = g * (d->chunks_per_group / d->world);
+		const int lc_end = (g + 1) * (d->chunks_per_group / d->world) < d->nlocal ? (g + 1) * (d->chunks_per_group / d->world) : d->nlocal;
+		sg.nlocal = lc_end > sg.lc_first ? lc_end - sg.lc_first : 0;
+		if ((rc = launch_shard_adam(sg, tt, h, 1.0f / (float)d->world, as))) return rc;
+	}
+	t->mark(9, as);
 	t->last_stage = 9;
 	t->ev_recorded = t->profiling && t->ev_ready;
 	return rc;

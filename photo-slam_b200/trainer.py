@@ -661,6 +661,12 @@ class DataParallelTrainer(GaussianTrainer):
     def status(self):
         return self.L.psb_dp_status(self.dp, torch.cuda.current_stream().cuda_stream) if self.mode == "p2p" else 0
 
+    def render(self, cam, out=None, radii=None, check=True):
+        """Forward only, on the complete replica: the owner-side Adam of the last step runs on the context's own stream and the peers
+        store their rows asynchronously, so the render is ordered behind both (device-side wait)."""
+        self.sync()
+        return super().render(cam, out, radii, check)
+
     def gather_moments(self):
         """Every rank receives the Adam moments of all rows (they are only maintained on the owner): call before
         densify/prune (which moves rows, hence owners) or before writing a checkpoint."""
