@@ -201,9 +201,10 @@ STAGE_KERNELS = {"preprocess": ["preprocess_fwd_kernel"], "depth_sort_scan": ["r
 SINGLE_KERNEL_STAGES = ("preprocess", "render_fwd", "render_bwd", "gaussian_backward", "frest_adam")
 
 
-def algorithmic_bytes(P, P_vis, N, W, H, T):
+def algorithmic_bytes(P, P_vis, N, W, H, T, P_touched=None):
     """Compulsory HBM bytes per stage of psb_trainer_step: SURVEY.md §8(d) per-unit figures x units of this workload, specialised to
     the fused design (the gradient never exists in memory). DESIGN.md §4 states the same numbers."""
+    P_t = P_vis if P_touched is None else P_touched   # Gaussians whose Adam state is live (a gradient reached them in this or an earlier step)
     return {
         "preprocess": 236 * P + 75 * P_vis + 8 * P,
         "depth_sort_scan": 4 * 16 * P + 8 * P,                 # 4 onesweep passes over (key,value) + offsets scan
@@ -211,12 +212,13 @@ def algorithmic_bytes(P, P_vis, N, W, H, T):
         "render_fwd": 4 * N + 48 * N + 20 * W * H + 8 * T,        # upper bound: whole list consumed
         "loss": (2 * 12 + 12) * W * H + 2 * 36 * W * H,
         "render_bwd": 4 * N + 48 * N + 20 * W * H + 36 * P_vis,
-        # Adam of the 14 small parameters (28 B each: read p, m, v; write p, m, v — the gradient is produced in registers) + the 9
-        # screen-space sums and the SH rows of the visible Gaussians (view-direction term of dL/dxyz) + visibility word
-        "gaussian_backward": 24 * 14 * P + (36 + 180 + 48) * P_vis + 16 * P,
-        # Adam of the [P,15,3] SH rows: read p, m, v, write p, m, v (24 B per parameter; the gradient is a product of two cached seeds) for the rows
-        # some view has reached; the others (zero gradient on zero moments: an exact no-op) only have their moments read (8 B per parameter)
-        "frest_adam": 24 * 45 * P_vis + 8 * 45 * (P - P_vis),
+        # Adam of the 14 small parameters (24 B each: read p, m, v; write p, m, v — the gradient is produced in registers) and the SH rows
+        # needed for the view-direction term of dL/dxyz, for the Gaussians a gradient has reached; for the others (hidden behind nearer
+        # splats or never in view: zero gradient on zero moments = an exact no-op of Adam) only the moments, to find that out; for every
+        # Gaussian the visibility word and its 48-byte row of screen-space sums
+        "gaussian_backward": (24 * 14 + 180) * P_t + 8 * 14 * (P - P_t) + (16 + 48) * P,
+        # Adam of the [P,15,3] SH rows: 24 B per parameter for live rows, 8 B (moments read) for the others
+        "frest_adam": 24 * 45 * P_t + 8 * 45 * (P - P_t),
     }
 
 
@@ -326,7 +328,7 @@ def run_psb(args, world, rank, local, dev):
     e1.record()
     torch.cuda.synchronize()
     render_ms = e0.elapsed_time(e1) / 10
-    stages, roof, stage_table, dp_stages = None, None, None, None
+    stages, roof, stage_table, dp_stages, P_touched = None, None, None, None, None
     peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -358,7 +360,8 @@ def run_psb(args, world, rank, local, dev):
         tr.set_profiling(False)
         stages = {k: float(np.mean(v)) for k, v in acc.items()}
         T_tiles = ((W + 15) // 16) * ((H + 15) // 16)
-        ab = algorithmic_bytes(P, P_vis, n_inst, W, H, T_tiles)
+        P_touched = int((model.exp_avg_sq_[2].flatten(1).abs().amax(dim=1) > 0).sum().item())
+        ab = algorithmic_bytes(P, P_vis, n_inst, W, H, T_tiles, P_touched)
         prof = ncu_profile_rows() if (P == 3_000_000 and args.camera == "replica") else {}
         sm_clock_ghz = (clocks.get("sm_mhz") or 1965.0) / 1e3
         stage_table = {}
@@ -401,6 +404,7 @@ def run_psb(args, world, rank, local, dev):
         "config": {"workload": f"{args.config}: synthetic {P} Gaussians (SURVEY 8d, seed 0), {W}x{H} {args.camera} intrinsics, SH degree 3, 1 view/GPU/step, "
                                "render + L1+0.2DSSIM + backward + densify stats + Adam(59 floats/Gaussian)",
                    "gaussians": P, "visible": P_vis, "num_rendered": n_inst, "width": W, "height": H,
+                   "optimizer_live_rows": P_touched if world == 1 else None,
                    "l2_policy": "working set (2.1 GB of parameters + moments per step) is larger than L2; no explicit flush",
                    "parallelism": "single GPU" if world == 1 else (
                        f"replicated scene, keyframe-sharded x{world}; fused NVLink step: 80 B gradient records pushed to the owner rank, sharded Adam, updated rows "

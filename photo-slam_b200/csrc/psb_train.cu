@@ -135,8 +135,9 @@ __global__ void __launch_bounds__(TB, PSB_A_MINBLOCKS) gaussian_backward_kernel(
 		sp_op = t.p[3][idx];
 		sp_rot = reinterpret_cast<const float4*>(t.p[5])[idx];
 		visible = tt != 0 && !overflow;
-		const float4 z = make_float4(0, 0, 0, 0);
-		sink[3 * idx] = z; sink[3 * idx + 1] = z; sink[3 * idx + 2] = z;  // ready for the next iteration
+		// ready for the next iteration (rows nothing was added to — culled or hidden Gaussians — are zero already: not rewritten)
+		const bool sink_dirty = s0.x != 0.f || s0.y != 0.f || s0.w != 0.f || s1.x != 0.f || s1.z != 0.f || s1.w != 0.f || s2.x != 0.f || s2.y != 0.f || s2.z != 0.f;
+		if (sink_dirty) { const float4 z = make_float4(0, 0, 0, 0); sink[3 * idx] = z; sink[3 * idx + 1] = z; sink[3 * idx + 2] = z; }
 		if (visible) {
 			// sink row: [0,1] mean2D.xy | [3,4,6] conic.xyw | [7] opacity | [8,9,10] rgb
 			const float2 dL_dmean2D = make_float2(s0.x, s0.y);
@@ -217,7 +218,19 @@ __global__ void __launch_bounds__(TB, PSB_A_MINBLOCKS) gaussian_backward_kernel(
 
 	// ---- the 14 small parameters of this Gaussian
 	if (valid) {
+		// a zero gradient on zero moments is an exact no-op of Adam (see frest_stream_kernel): hidden / never-reached Gaussians are not rewritten
+		bool idle = false;
 		if (ADAM) {
+			bool nz = g_xyz.x != 0.f || g_xyz.y != 0.f || g_xyz.z != 0.f || g_dc.x != 0.f || g_dc.y != 0.f || g_dc.z != 0.f || g_scale.x != 0.f ||
+			          g_scale.y != 0.f || g_scale.z != 0.f || g_opac != 0.f || g_rot.x != 0.f || g_rot.y != 0.f || g_rot.z != 0.f || g_rot.w != 0.f ||
+			          mo != 0.f || vo != 0.f || mr.x != 0.f || mr.y != 0.f || mr.z != 0.f || mr.w != 0.f || vr.x != 0.f || vr.y != 0.f || vr.z != 0.f || vr.w != 0.f;
+#pragma unroll
+			for (int a = 0; a < 3; a++)
+#pragma unroll
+				for (int c = 0; c < 3; c++) nz = nz || m3[a][c] != 0.f || v3[a][c] != 0.f;
+			idle = !nz;
+		}
+		if (ADAM && !idle) {
 			const float gx[3] = {g_xyz.x, g_xyz.y, g_xyz.z}, gd[3] = {g_dc.x, g_dc.y, g_dc.z}, gs[3] = {g_scale.x, g_scale.y, g_scale.z};
 #pragma unroll
 			for (int c = 0; c < 3; c++) {
@@ -434,31 +447,44 @@ __global__ void __launch_bounds__(TB) shard_adam_small_kernel(DpShard d, TrainTe
 		}
 		const float gs = grad_scale;
 		const float lx = h.lr[0] * ac.inv_bc1, ld = h.lr[1] * ac.inv_bc1, lo = h.lr[3] * ac.inv_bc1, ls = h.lr[4] * ac.inv_bc1, lrr = h.lr[5] * ac.inv_bc1;
+		// zero gradient on zero moments = an exact no-op of Adam: nothing to store locally, nothing to send (hidden / never-reached Gaussians)
+		bool live = mo != 0.f || vo != 0.f || mr.x != 0.f || mr.y != 0.f || mr.z != 0.f || mr.w != 0.f || vr.x != 0.f || vr.y != 0.f || vr.z != 0.f || vr.w != 0.f;
 #pragma unroll
-		for (int c = 0; c < 3; c++) {
-			adam1(sp_xyz[c], m3[0][c], v3[0][c], acc[c] * gs, lx, ac);
-			adam1(sp_dc[c], m3[1][c], v3[1][c], acc[3 + c] * gs, ld, ac);
-			adam1(sp_sc[c], m3[2][c], v3[2][c], acc[7 + c] * gs, ls, ac);
-		}
-		adam1(sp_op, mo, vo, acc[6] * gs, lo, ac);
-		adam1(sp_rot.x, mr.x, vr.x, acc[10] * gs, lrr, ac);
-		adam1(sp_rot.y, mr.y, vr.y, acc[11] * gs, lrr, ac);
-		adam1(sp_rot.z, mr.z, vr.z, acc[12] * gs, lrr, ac);
-		adam1(sp_rot.w, mr.w, vr.w, acc[13] * gs, lrr, ac);
+		for (int i = 0; i < 14; i++) live = live || acc[i] != 0.f;
 #pragma unroll
-		for (int c = 0; c < 3; c++) {
-			t.m[0][3 * idx + c] = m3[0][c]; t.v[0][3 * idx + c] = v3[0][c];
-			t.m[1][3 * idx + c] = m3[1][c]; t.v[1][3 * idx + c] = v3[1][c];
-			t.m[4][3 * idx + c] = m3[2][c]; t.v[4][3 * idx + c] = v3[2][c];
-		}
-		t.m[3][idx] = mo; t.v[3][idx] = vo;
-		reinterpret_cast<float4*>(t.m[5])[idx] = mr; reinterpret_cast<float4*>(t.v[5])[idx] = vr;
-		for (int j = 0; j < d.world; j++) {  // all-gather by remote stores: every replica receives the updated rows
-			float* const* pp = d.param[j];
+		for (int a = 0; a < 3; a++)
 #pragma unroll
-			for (int c = 0; c < 3; c++) { pp[0][3 * idx + c] = sp_xyz[c]; pp[1][3 * idx + c] = sp_dc[c]; pp[4][3 * idx + c] = sp_sc[c]; }
-			pp[3][idx] = sp_op;
-			reinterpret_cast<float4*>(pp[5])[idx] = sp_rot;
+			for (int c = 0; c < 3; c++) live = live || m3[a][c] != 0.f || v3[a][c] != 0.f;
+		if (live) {
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				adam1(sp_xyz[c], m3[0][c], v3[0][c], acc[c] * gs, lx, ac);
+				adam1(sp_dc[c], m3[1][c], v3[1][c], acc[3 + c] * gs, ld, ac);
+				adam1(sp_sc[c], m3[2][c], v3[2][c], acc[7 + c] * gs, ls, ac);
+			}
+			adam1(sp_op, mo, vo, acc[6] * gs, lo, ac);
+			adam1(sp_rot.x, mr.x, vr.x, acc[10] * gs, lrr, ac);
+			adam1(sp_rot.y, mr.y, vr.y, acc[11] * gs, lrr, ac);
+			adam1(sp_rot.z, mr.z, vr.z, acc[12] * gs, lrr, ac);
+			adam1(sp_rot.w, mr.w, vr.w, acc[13] * gs, lrr, ac);
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				t.m[0][3 * idx + c] = m3[0][c]; t.v[0][3 * idx + c] = v3[0][c];
+				t.m[1][3 * idx + c] = m3[1][c]; t.v[1][3 * idx + c] = v3[1][c];
+				t.m[4][3 * idx + c] = m3[2][c]; t.v[4][3 * idx + c] = v3[2][c];
+			}
+			t.m[3][idx] = mo; t.v[3][idx] = vo;
+			reinterpret_cast<float4*>(t.m[5])[idx] = mr; reinterpret_cast<float4*>(t.v[5])[idx] = vr;
+			// all-gather by remote stores: every replica receives the updated rows. Destinations are visited starting at rank + 1 so that, at
+			// any moment, the ranks (which run this kernel in step) aim at different receivers instead of all at the same one.
+			for (int jj = 0; jj < d.world; jj++) {
+				const int j = d.rotate ? (d.rank + 1 + jj) % d.world : jj;
+				float* const* pp = d.param[j];
+#pragma unroll
+				for (int c = 0; c < 3; c++) { pp[0][3 * idx + c] = sp_xyz[c]; pp[1][3 * idx + c] = sp_dc[c]; pp[4][3 * idx + c] = sp_sc[c]; }
+				pp[3][idx] = sp_op;
+				reinterpret_cast<float4*>(pp[5])[idx] = sp_rot;
+			}
 		}
 	}
 	// summed f_rest gradient row -> local scratch (coalesced through shared memory; row stride 45 words is conflict-free)
@@ -498,7 +524,10 @@ __global__ void __launch_bounds__(256) shard_adam_frest_kernel(DpShard d, TrainT
 			adam1(pp.z, mm.z, vv.z, gg.z, lr_eff, ac);
 			adam1(pp.w, mm.w, vv.w, gg.w, lr_eff, ac);
 			__stcs(reinterpret_cast<float4*>(m + e), mm); __stcs(reinterpret_cast<float4*>(v + e), vv);
-			for (int j = 0; j < d.world; j++) *reinterpret_cast<float4*>(d.param[j][2] + e) = pp;
+			for (int jj = 0; jj < d.world; jj++) {
+				const int j = d.rotate ? (d.rank + 1 + jj) % d.world : jj;
+				*reinterpret_cast<float4*>(d.param[j][2] + e) = pp;
+			}
 		} else {  // < 4 trailing elements (P * 45 not a multiple of 4)
 			for (size_t k = e; k < e_end; k++) {
 				float pp = p[k], mm = m[k], vv = v[k];
@@ -615,13 +644,14 @@ int launch_push_backward(int first, int P, const TrainTensors& t, const Camera& 
 	return 0;
 }
 
-int launch_shard_adam(const DpShard& d, const TrainTensors& t, const StepHyper& h, float grad_scale, cudaStream_t stream)
+int launch_shard_adam(const DpShard& d, const TrainTensors& t, const StepHyper& h, float grad_scale, cudaStream_t stream, cudaEvent_t between)
 {
 	AdamCoef ac;
 	ac.beta1 = h.beta1; ac.beta2 = h.beta2; ac.eps = h.eps; ac.inv_bc1 = h.inv_bc1; ac.inv_bc2_sqrt = 1.0f / h.bc2_sqrt;
 	if (d.nlocal > 0) {  // owned chunks [lc_first, lc_first + nlocal) of this pipeline group
 		shard_adam_small_kernel<<<d.nlocal, TB, 0, stream>>>(d, t, h, grad_scale);
 		PSB_LAUNCH_OK();
+		if (between) cudaEventRecord(between, stream);
 		shard_adam_frest_kernel<<<d.nlocal, 256, 0, stream>>>(d, t, h.lr[2] * ac.inv_bc1, ac);
 		PSB_LAUNCH_OK();
 	}

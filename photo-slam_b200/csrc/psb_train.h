@@ -54,12 +54,13 @@ struct DpShard {             // what the owner-side Adam kernels need
 	uint32_t* done_counter;            // local
 	int world, rank, nlocal_max, nlocal, P;   // nlocal: owned chunks handled by this launch, starting at local chunk lc_first
 	int lc_first;
+	int rotate;                        // 1: each rank walks the destination ranks starting at rank + 1 (PSB_DP_ROTATE=0: all start at rank 0)
 	uint32_t epoch;
 	int fence_in_kernel;               // as in DpPush
 };
 int launch_push_backward(int first, int P, const TrainTensors& t, const Camera& cam, const GeomState& geom, float* sink, const StepHyper& h,
                          const DensifyStats& st, const uint32_t* counters, uint32_t capacity, const DpPush& dp, cudaStream_t stream);
-int launch_shard_adam(const DpShard& d, const TrainTensors& t, const StepHyper& h, float grad_scale, cudaStream_t stream);
+int launch_shard_adam(const DpShard& d, const TrainTensors& t, const StepHyper& h, float grad_scale, cudaStream_t stream, cudaEvent_t between = nullptr);
 // spins (device side) until flags[0..world) >= epoch (world <= 64 words); after `timeout_ms` writes 1 to *status and gives up
 int launch_wait_flags(const uint32_t* flags, int world, uint32_t epoch, uint32_t* status, cudaStream_t stream);
 

@@ -38,7 +38,7 @@ struct psb_trainer {
 	//   fused step:        7 per-Gaussian backward kernel | 8 f_rest Adam stream kernel
 	//   data-parallel step: 7 push backward | 8 wait for every rank's records | 9 owner-side Adam (+ stores to every replica);
 	//                       ev[NSTAGE] is recorded BEFORE the wait for the previous step's rows (stage "wait_params" = ev[NSTAGE] -> ev[0])
-	static constexpr int NSTAGE = 10;
+	static constexpr int NSTAGE = 11;   // (ev[10]: between the two owner-side Adam kernels of the data-parallel step)
 	int last_stage = 0;  // index of the last boundary the last profiled call recorded
 	cudaEvent_t ev[NSTAGE + 1] = {};
 	bool ev_ready = false, ev_recorded = false;
@@ -418,6 +418,8 @@ int psb_dp_step(psb_trainer* t, psb_dp* d, int P, int M, const psb_model* model,
 	sh.meta = reinterpret_cast<const float*>(d->base + d->off_meta);
 	sh.g_rest = d->g_rest; sh.done_counter = d->local + 1;
 	sh.world = d->world; sh.rank = d->rank; sh.nlocal_max = d->nlocal_max; sh.P = P; sh.epoch = epoch;
+	static const int rotate = (getenv("PSB_DP_ROTATE") && atoi(getenv("PSB_DP_ROTATE")) == 0) ? 0 : 1;
+	sh.rotate = rotate;
 	// Pipeline over groups of chunks: [main stream] push backward of group g (records go straight into the owners' inboxes) + signal;
 	// [adam stream] wait until every rank's records of group g have landed -> Adam of the owned rows of group g, updated rows stored to
 	// every replica + signal. With one group everything stays on the main stream. Flag word of (group g, rank r) = g * world + r.
@@ -438,7 +440,7 @@ int psb_dp_step(psb_trainer* t, psb_dp* d, int P, int M, const psb_model* model,
 		sg.lc_first = g * (d->chunks_per_group / d->world);
 		const int lc_end = (g + 1) * (d->chunks_per_group / d->world) < d->nlocal ? (g + 1) * (d->chunks_per_group / d->world) : d->nlocal;
 		sg.nlocal = lc_end > sg.lc_first ? lc_end - sg.lc_first : 0;
-		if ((rc = launch_shard_adam(sg, tt, h, 1.0f / (float)d->world, as))) return rc;
+		if ((rc = launch_shard_adam(sg, tt, h, 1.0f / (float)d->world, as, (t->profiling && t->ev_ready && g == d->groups - 1) ? t->ev[10] : nullptr))) return rc;
 	}
 	t->mark(9, as);
 	t->last_stage = 9;
@@ -658,6 +660,7 @@ int psb_trainer_stage_times(psb_trainer* t, float* ms, int n)
 	int filled = 0;
 	for (int i = 0; i < t->last_stage && i < n; i++, filled++) PSB_CUDA_OK(cudaEventElapsedTime(&ms[i], t->ev[i], t->ev[i + 1]));
 	if (t->last_stage == 9 && n > 9) { PSB_CUDA_OK(cudaEventElapsedTime(&ms[9], t->ev[psb_trainer::NSTAGE], t->ev[0])); filled = 10; }
+	if (t->last_stage == 9 && n > 10) { PSB_CUDA_OK(cudaEventElapsedTime(&ms[10], t->ev[10], t->ev[9])); filled = 11; }   // the f_rest kernel + signal alone
 	return filled;
 }
 

@@ -511,7 +511,8 @@ class GaussianTrainer:
         torch.cuda.current_stream().synchronize()
 
     STAGES = ("preprocess", "depth_sort_scan", "binning", "render_fwd", "loss", "render_bwd", "gaussian_backward", "frest_adam")
-    DP_STAGES = ("preprocess", "depth_sort_scan", "binning", "render_fwd", "loss", "render_bwd", "push_backward", "wait_grads", "shard_adam", "wait_params")
+    DP_STAGES = ("preprocess", "depth_sort_scan", "binning", "render_fwd", "loss", "render_bwd", "push_backward", "wait_grads", "shard_adam", "wait_params",
+                 "shard_adam_frest_part")
 
     def set_profiling(self, enable=True):
         self.L.psb_trainer_set_profiling.argtypes = [C.c_void_p, C.c_int]
@@ -519,10 +520,10 @@ class GaussianTrainer:
 
     def stage_times(self):
         """ms per stage of the last profiled step (CUDA events on the step's stream)."""
-        ms = (C.c_float * 10)()
+        ms = (C.c_float * 11)()
         self.L.psb_trainer_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
-        n = _lib.check(self.L.psb_trainer_stage_times(self.h, ms, 10), "psb_trainer_stage_times")
-        names = self.DP_STAGES if n == 10 else self.STAGES
+        n = _lib.check(self.L.psb_trainer_stage_times(self.h, ms, 11), "psb_trainer_stage_times")
+        names = self.DP_STAGES if n >= 10 else self.STAGES
         return dict(zip(names[:n], [float(x) for x in ms][:n]))
 
     def trainingOnce(self, cam, gt_image, mask=None):
