@@ -420,6 +420,8 @@ int psb_dp_step(psb_trainer* t, psb_dp* d, int P, int M, const psb_model* model,
 	sh.world = d->world; sh.rank = d->rank; sh.nlocal_max = d->nlocal_max; sh.P = P; sh.epoch = epoch;
 	static const int rotate = (getenv("PSB_DP_ROTATE") && atoi(getenv("PSB_DP_ROTATE")) == 0) ? 0 : 1;
 	sh.rotate = rotate;
+	static const int bulk = (getenv("PSB_DP_BULK") && atoi(getenv("PSB_DP_BULK")) == 0) ? 0 : 1;
+	sh.bulk = bulk;
 	// Pipeline over groups of chunks: [main stream] push backward of group g (records go straight into the owners' inboxes) + signal;
 	// [adam stream] wait until every rank's records of group g have landed -> Adam of the owned rows of group g, updated rows stored to
 	// every replica + signal. With one group everything stays on the main stream. Flag word of (group g, rank r) = g * world + r.
