@@ -90,3 +90,32 @@ def test_libtorch_cpu_sh_baseline_matches_the_host_sh_utils():
         a = ref_sh_loss_cpu.eval_sh(deg, torch.from_numpy(sh), torch.from_numpy(d)).numpy()
         b = su.eval_sh(deg, sh, d)
         assert np.allclose(a, b, rtol=1e-5, atol=1e-6), deg
+
+
+def test_renderer_covariance_activation_matches_the_closed_form():
+    """renderer.get_covariance_activation (GaussianModel::getCovarianceActivation, reference src/gaussian_model.cpp:73-101) on CPU tensors:
+    Sigma = R diag(s)^2 R^T with R from the normalised quaternion, upper triangle in the rasterizer's order [xx, xy, xz, yy, yz, zz]."""
+    import numpy as np
+    import torch
+    from photo_slam_b200 import renderer
+
+    class M:
+        pass
+    rng = np.random.default_rng(0)
+    m = M()
+    q = rng.normal(size=(50, 4)).astype(np.float32)
+    s = rng.normal(0, 0.3, size=(50, 3)).astype(np.float32)
+    m.rotation_, m.scaling_ = torch.from_numpy(q), torch.from_numpy(s)
+    got = renderer.get_covariance_activation(m, 1.3).numpy()
+    qn = q / np.linalg.norm(q, axis=1, keepdims=True)
+    w, x, y, z = qn.T
+    R = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)], 1),
+                  np.stack([2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)], 1),
+                  np.stack([2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], 1)], 1)
+    S2 = (1.3 * np.exp(s)) ** 2
+    cov = np.einsum("nij,nj,nkj->nik", R, S2, R)
+    exp = np.stack([cov[:, 0, 0], cov[:, 0, 1], cov[:, 0, 2], cov[:, 1, 1], cov[:, 1, 2], cov[:, 2, 2]], 1)
+    assert np.allclose(got, exp, rtol=1e-5, atol=1e-6)
+    f = M()
+    f.features_dc_, f.features_rest_ = torch.zeros(4, 1, 3), torch.ones(4, 8, 3)
+    assert renderer.get_features(f).shape == (4, 9, 3)
