@@ -394,9 +394,9 @@ def run_psb(args, world, rank, local, dev):
                                     "frac_fused_minimum": (ab["gaussian_backward"] + ab["frest_adam"]) / 1e6 / (stages["gaussian_backward"] + stages["frest_adam"]) / peak,
                                     "frac_survey_8d": (1652 * P + 559 * P_vis) / 1e6 / (stages["gaussian_backward"] + stages["frest_adam"]) / peak}}
 
-    # kernels of this library per iteration (memsets not counted). p2p: 17 up to the tile backward + param-flag wait + push backward
-    # + grad-flag wait + 2 owner-side Adam kernels; nccl: 4 slabs x (2 backward + 6 Adam)
-    launches_per_step = 19 if world == 1 else (17 + 5 if dp_mode == "p2p" else 17 + 4 * (2 + 6))
+    # kernels of this library per iteration (memsets not counted). p2p: the 17 launches up to the tile backward + wait for the previous
+    # step's rows + push backward + signal + wait for the records + 2 owner-side Adam kernels + signal; nccl: 4 slabs x (2 backward + 6 Adam)
+    launches_per_step = 19 if world == 1 else (17 + 7 if dp_mode == "p2p" else 17 + 4 * (2 + 6))
     out = {
         "metric": "train_iters_per_sec", "value": world * 1000.0 / ms_step, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

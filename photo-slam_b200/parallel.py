@@ -113,3 +113,61 @@ class SlabGradBuffer:
         """Base addresses such that row g of tensor i lands at blocks(s)[i][(g - first) * SIZES[i]] (see psb_trainer_backward_slab)."""
         first, _ = self.slabs[s]
         return [b.data_ptr() - first * k * 4 for b, k in zip(self.blocks(s), SIZES)]
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Host-side specification of the record protocol of the NVLink data-parallel step (csrc/psb_train.cu:
+# gaussian_backward_kernel<PUSH>, shard_adam_small_kernel; DESIGN.md §8). Device-agnostic torch code: the CPU / gloo test
+# tests/test_parallel_cpu.py runs the whole step with it (per-rank gradients from the C oracle), and it documents what the
+# kernels exchange: per Gaussian that received a gradient, ONE 80-byte record
+#     [ g_xyz 3 | g_f_dc 3 | g_opacity 1 | g_scaling 3 | g_rotation 4 | masked dL/dRGB 3 | pad 2 | epoch ]
+# The 45 f_rest gradients are not sent: they are the rank-1 product  w_k(dir) * dL/dRGB[ch]  (reference backward.cu:20-139), and
+# the owner re-evaluates w_k from its own copy of xyz and the sender's camera centre.
+# ------------------------------------------------------------------------------------------------------------------------
+REC_FLOATS = 20
+_SH_C0 = 0.28209479177387814
+_SH_C1 = 0.4886025119029199
+_SH_C2 = (1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396)
+_SH_C3 = (-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658, 1.445305721320277,
+          -0.5900435899266435)
+
+
+def sh_basis_weights(xyz, campos, degree):
+    """[P, 16] weights dRGB/dsh_k of the real SH basis along normalize(xyz - campos); columns beyond (degree+1)^2 are zero."""
+    d = xyz - campos.reshape(1, 3)
+    d = d / torch.sqrt((d * d).sum(dim=1, keepdim=True))
+    x, y, z = d[:, 0], d[:, 1], d[:, 2]
+    xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+    w = [torch.full_like(x, _SH_C0), -_SH_C1 * y, _SH_C1 * z, -_SH_C1 * x,
+         _SH_C2[0] * xy, _SH_C2[1] * yz, _SH_C2[2] * (2.0 * zz - xx - yy), _SH_C2[3] * xz, _SH_C2[4] * (xx - yy),
+         _SH_C3[0] * y * (3.0 * xx - yy), _SH_C3[1] * xy * z, _SH_C3[2] * y * (4.0 * zz - xx - yy), _SH_C3[3] * z * (2.0 * zz - 3.0 * xx - 3.0 * yy),
+         _SH_C3[4] * x * (4.0 * zz - xx - yy), _SH_C3[5] * z * (xx - yy), _SH_C3[6] * x * (xx - 3.0 * yy)]
+    w = torch.stack(w, dim=1)
+    w[:, (degree + 1) ** 2:] = 0.0
+    return w
+
+
+def pack_records(grads, masked_drgb, epoch):
+    """grads: the six raw-parameter gradients of ONE view (reference shapes; features_rest is ignored), masked_drgb [P,3] = clamp-masked
+    dL/dRGB. -> [P, 20] float32 records; rows without any gradient carry epoch 0 (= not sent)."""
+    P = grads[0].size(0)
+    rec = torch.zeros((P, REC_FLOATS), dtype=torch.float32, device=grads[0].device)
+    rec[:, 0:3], rec[:, 3:6], rec[:, 6:7] = grads[0], grads[1].reshape(P, 3), grads[3].reshape(P, 1)
+    rec[:, 7:10], rec[:, 10:14], rec[:, 14:17] = grads[4], grads[5], masked_drgb
+    sends = rec[:, :17].abs().sum(dim=1) > 0
+    rec[:, 19] = torch.where(sends, torch.full((P,), float(epoch)), torch.zeros(P)).to(rec.device)
+    return rec
+
+
+def reduce_records(records, xyz, campos_all, degree, epoch):
+    """Owner side: records = [world][P_owned, 20] of the rows this rank owns, xyz [P_owned, 3], campos_all [world, 3].
+    -> the six summed raw-parameter gradients of those rows (features_rest reconstructed from the basis weights)."""
+    n = xyz.size(0)
+    acc = torch.zeros((n, 14), dtype=torch.float32, device=xyz.device)
+    g_rest = torch.zeros((n, 15, 3), dtype=torch.float32, device=xyz.device)
+    for s, rec in enumerate(records):
+        live = (rec[:, 19] == float(epoch)).unsqueeze(1).float()      # stale epoch word: rank s sent nothing for that row
+        acc += rec[:, :14] * live
+        w = sh_basis_weights(xyz, campos_all[s], degree)[:, 1:]       # [n, 15]
+        g_rest += w.unsqueeze(2) * (rec[:, 14:17] * live).unsqueeze(1)
+    return [acc[:, 0:3], acc[:, 3:6].reshape(n, 1, 3), g_rest, acc[:, 6:7], acc[:, 7:10], acc[:, 10:14]]
