@@ -54,7 +54,7 @@ struct DpShard {             // what the owner-side Adam kernels need
 	uint32_t* done_counter;            // local
 	int world, rank, nlocal_max, nlocal, P;   // nlocal: owned chunks handled by this launch, starting at local chunk lc_first
 	int lc_first;
-	int bulk;                          // 1: the small-parameter chunks leave as TMA bulk stores (PSB_DP_BULK=0: per-thread 16-byte stores)
+	int bulk;                          // 1 (PSB_DP_BULK=1): the small-parameter chunks leave as TMA bulk stores; 0 (default): per-thread 16-byte stores
 	int rotate;                        // 1: each rank walks the destination ranks starting at rank + 1 (PSB_DP_ROTATE=0: all start at rank 0)
 	uint32_t epoch;
 	int fence_in_kernel;               // as in DpPush
