@@ -2,7 +2,7 @@
 Per tile row the set of dx with min_dy q(dx, dy) <= t is an interval [xl, xr] with a closed form (two square roots per row);
 a tile of the row is kept iff its dx-range meets the interval. Checked here against the per-tile test (tests/test_cull_cpu.py)
 and a brute-force per-pixel evaluation: identical cull sets (to 2 in 14k tiles), never drops a contributing tile.
-Not yet ported to csrc/psb_common.cuh (TileCull::rect_mask). Usage: python tools/proto_row_extent_mask.py"""
+Ported to csrc/psb_common.cuh (TileCull::rect_mask) in round 2; tests/test_cull_cpu.py holds the maintained numpy specification. Usage: python tools/proto_row_extent_mask.py"""
 import sys, numpy as np
 sys.path[:0]=['.','oracle','tests']
 import oracle_c
