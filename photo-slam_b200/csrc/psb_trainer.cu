@@ -357,7 +357,7 @@ int psb_dp_destroy(psb_dp* d)
 int psb_dp_sync(psb_dp* d, void* stream_)
 {
 	if (!d) { set_error_msg("psb_dp_sync: null"); return PSB_ERR_ARG; }
-	if (d->epoch == 0 || (d->world == 1 && d->groups == 1)) return 0;   // (one rank, one group: everything is on the caller's stream)
+	if (d->epoch == 0 || d->P == 0 || (d->world == 1 && d->groups == 1)) return 0;   // (one rank, one group: everything is on the caller's stream)
 	return launch_wait_flags(reinterpret_cast<const uint32_t*>(d->base + d->off_pflag), d->groups * d->world, d->epoch, d->local + 2, (cudaStream_t)stream_);
 }
 
@@ -386,7 +386,7 @@ int psb_dp_step(psb_trainer* t, psb_dp* d, int P, int M, const psb_model* model,
 	const uint32_t epoch = ++d->epoch;
 	t->mark(psb_trainer::NSTAGE, stream);
 	// every rank's updated rows of the previous step must have landed here before this step reads the parameters
-	if (epoch > 1 && (d->world > 1 || d->groups > 1))   // (also orders this step behind the previous step's work on the adam stream)
+	if (epoch > 1 && P > 0 && (d->world > 1 || d->groups > 1))   // (also orders this step behind the previous step's work on the adam stream)
 		if ((rc = launch_wait_flags(reinterpret_cast<const uint32_t*>(d->base + d->off_pflag), d->groups * d->world, epoch - 1, d->local + 2, stream))) return rc;
 	// render, loss, tile backward (the 9 screen-space sums per Gaussian)
 	if ((rc = step_impl(t, P, M, model, camera, background, gt_image, mask, step, out_color, radii, nullptr, stream, /*tiles_only=*/true))) return rc;
