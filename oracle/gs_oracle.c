@@ -926,4 +926,21 @@ void orc_reset_opacity(int P, float* opacity)
 	}
 }
 
-int orc_version(void) { return 2; }
+/* ---------------- Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11) — the counter-based
+ * generator the fused densify kernel draws its split samples from (csrc/psb_densify.cu:philox4x32_10, same round structure and constants).
+ * Pinned by the Random123 known-answer vectors in tests/test_oracle_cpu.py. ctr[4], key[2] -> out[4]. */
+void orc_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out)
+{
+	const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+	uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+	for (int r = 0; r < 10; r++) {
+		const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+		const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+		const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+		c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+		k0 += W0; k1 += W1;
+	}
+	out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+int orc_version(void) { return 3; }

@@ -170,3 +170,18 @@ def test_reset_opacity_oracle_matches_aten():
     o = np.random.default_rng(0).normal(0, 2, (500, 1)).astype(np.float32)
     st = ref_densify.reset_opacity(dict(p=[None, None, None, torch.from_numpy(o.copy())], m=[None] * 6, v=[None] * 6))
     assert np.allclose(oracle_c.reset_opacity(o), st["p"][3].numpy(), rtol=1e-6, atol=1e-6)
+
+
+def test_philox4x32_10_known_answer_vectors():
+    """oracle/gs_oracle.c:orc_philox4x32_10 — the restatement of csrc/psb_densify.cu:philox4x32_10 (same rounds, same constants) — against the
+    Random123 known-answer vectors of Philox4x32-10 (Salmon et al., SC'11; kat_vectors of the Random123 distribution)."""
+    import ctypes as C
+    L = oracle_c.lib()
+
+    def ph(ctr, key):
+        c, k, o = (C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), (C.c_uint32 * 4)()
+        L.orc_philox4x32_10(c, k, o)
+        return list(o)
+    assert ph([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert ph([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert ph([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
