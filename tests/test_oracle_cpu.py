@@ -185,3 +185,42 @@ def test_philox4x32_10_known_answer_vectors():
     assert ph([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
     assert ph([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert ph([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_tile_backward_moment_identities():
+    """The algebra behind render_bwd_kernel's round-2 formulation, checked in float64 against the reference's per-pixel expressions
+    (cuda_rasterizer/backward.cu:497-547): (1) the nine per-Gaussian sums from six moments of w = G dL/dG + three colour sums;
+    (2) dL/dalpha from the scalar recursion on dot(accum_rec, dL/dpixel) instead of the 3-vector recursion."""
+    rng = np.random.default_rng(0)
+    n = 257                                    # pixels touched by one Gaussian in one tile
+    A, B, Cc, o = 0.31, -0.07, 0.22, 0.6       # conic, opacity
+    W, H = 1200, 680
+    ddelx_dx, ddely_dy = 0.5 * W, 0.5 * H
+    dx, dy = rng.normal(0, 4, n), rng.normal(0, 4, n)
+    G = np.exp(-0.5 * (A * dx * dx + Cc * dy * dy) - B * dx * dy)
+    dL_dalpha = rng.normal(0, 1, n)
+    dL_dG = o * dL_dalpha
+    # reference, per pixel (backward.cu:518-547)
+    gdx, gdy = G * dx, G * dy
+    dG_ddelx = -gdx * A - gdy * B
+    dG_ddely = -gdy * Cc - gdx * B
+    ref = [np.sum(dL_dG * dG_ddelx * ddelx_dx), np.sum(dL_dG * dG_ddely * ddely_dy), np.sum(-0.5 * gdx * dx * dL_dG),
+           np.sum(-0.5 * gdx * dy * dL_dG), np.sum(-0.5 * gdy * dy * dL_dG), np.sum(G * dL_dalpha)]
+    # moments of w
+    w = dL_dG * G
+    M0, Mx, My, Mxx, Mxy, Myy = w.sum(), (w * dx).sum(), (w * dy).sum(), (w * dx * dx).sum(), (w * dx * dy).sum(), (w * dy * dy).sum()
+    mine = [-(A * Mx + B * My) * ddelx_dx, -(Cc * My + B * Mx) * ddely_dy, -0.5 * Mxx, -0.5 * Mxy, -0.5 * Myy, M0 / o]
+    assert np.allclose(mine, ref, rtol=1e-12, atol=1e-12)
+    # (2) back-to-front sweep of one pixel over k contributors: vector recursion vs its dot product with dL/dpixel
+    k = 40
+    col, alpha = rng.uniform(0, 1, (k, 3)), rng.uniform(0.01, 0.6, k)
+    dLdp = rng.normal(0, 1, 3)
+    accum, last_alpha, last_color = np.zeros(3), 0.0, np.zeros(3)
+    acc_dot, last_cdot = 0.0, 0.0
+    for i in range(k):
+        accum = last_alpha * last_color + (1.0 - last_alpha) * accum                 # backward.cu:503
+        ref_dalpha = np.sum((col[i] - accum) * dLdp)                                 # :505-508 (before the * T factor)
+        cdot = float(np.dot(col[i], dLdp))
+        acc_dot = last_alpha * last_cdot + (1.0 - last_alpha) * acc_dot
+        assert abs((cdot - acc_dot) - ref_dalpha) < 1e-12
+        last_color, last_alpha, last_cdot = col[i], alpha[i], cdot
