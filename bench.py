@@ -59,9 +59,14 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     MASKS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
-        self.index, self.samples, self.stop = index, [], False
+    def __init__(self, index, active=True, interval=0.005):
+        # active=False (ranks > 0 of a multi-GPU run): no thread, no NVML traffic. Eight processes polling NVML every 5 ms measurably slowed the
+        # queued-launch leg at N = 8 (value 3-9 % below the e2e leg of the same run; equal at a 20 ms period): rank 0 alone samples, every 20 ms.
+        self.index, self.samples, self.stop, self.active, self.interval = index, [], False, active, interval
         self.nvml = None
+        if not active:
+            self.t = None
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -98,15 +103,17 @@ class ClockSampler:
                     self.samples.append(smp)
             except Exception:
                 pass
-            time.sleep(0.005 if self.nvml is not None else 0.5)
+            time.sleep(self.interval if self.nvml is not None else 0.5)
 
     def __enter__(self):
-        self.t.start()
+        if self.t is not None:
+            self.t.start()
         return self
 
     def __exit__(self, *a):
         self.stop = True
-        self.t.join(timeout=6)
+        if self.t is not None:
+            self.t.join(timeout=6)
 
     def summary(self):
         if not self.samples:
@@ -271,7 +278,7 @@ def run_psb(args, world, rank, local, dev):
 
     # --- value: K iterations, inputs resident in HBM, no host sync inside (parameters + moments = 2.1 GB >> L2)
     barrier(world)
-    with ClockSampler(local) as clk:
+    with ClockSampler(local, active=(rank == 0), interval=0.005 if world == 1 else 0.02) as clk:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
